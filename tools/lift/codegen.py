@@ -1,0 +1,197 @@
+"""Turn a traced plant graph (symtrace.py) into C / CUDA source.
+
+Output = two text blobs:
+  * tables:  `PLANT_TABLE(name, n) = {...};` for every breakpoint / value / slope array that survives
+  * body:    straight-line SSA statements computing xdot[] from X[] and U[]
+
+Passes: dead-code elimination from the live derivative outputs; lookup specialisation (a 2-D lookup whose
+first argument is a constant collapses to a 1-D lookup over a pre-blended column; slope tables are
+pre-divided in double with the reference's operation order so results stay bit-identical); sharing of
+the breakpoint search between lookups on the same (axis, input).
+"""
+import symtrace as S
+
+
+def hexf(x):
+    if x != x:
+        return '(0.0/0.0)'
+    if x in (float('inf'), float('-inf')):
+        return '(1.0/0.0)' if x > 0 else '(-1.0/0.0)'
+    return float(x).hex()
+
+
+class Emitter:
+    def __init__(self, tracer, real='real'):
+        self.tr = tracer
+        self.tabs = {}        # name -> list of floats
+        self.tabname = {}     # key -> name
+        self.lines = []
+        self.real = real
+        self.idx = {}         # (axis name, node id) -> (ivar, dvar)
+        self.stats = {}
+
+    # ---- tables ----
+    def table(self, key, prefix='T'):
+        if key not in self.tabname:
+            name = '%s%d' % (prefix, len(self.tabname))
+            self.tabname[key] = name
+            self.tabs[name] = list(self.tr.tables[key]) if key in self.tr.tables else list(key[1])
+        return self.tabname[key]
+
+    def derived(self, tag, vals):
+        key = ('derived', tuple(vals), tag)
+        if key not in self.tabname:
+            name = 'D%d' % len(self.tabname)
+            self.tabname[key] = name
+            self.tabs[name] = list(vals)
+        return self.tabname[key]
+
+    # ---- helpers ----
+    def ref(self, a):
+        if S.is_sym(a):
+            if a.op == 'const':
+                return hexf(S.fval(a.args[0]))
+            return 'v%d' % a.id
+        return hexf(S.fval(a))
+
+    def index_of(self, axis_key, unode):
+        axis = self.table(axis_key)
+        n = len(self.tabs[axis])
+        k = (axis, unode.id)
+        if k not in self.idx:
+            iv = 'i%d' % len(self.idx)
+            dv = 'd%d' % len(self.idx)
+            self.lines.append('const int %s = plant_index(PLANT_TAB(%s), %d, %s);' % (iv, axis, n, self.ref(unode)))
+            self.lines.append('const %s %s = %s - PLANT_TAB(%s)[%s];' % (self.real, dv, self.ref(unode), axis, iv))
+            self.idx[k] = (iv, dv)
+        return self.idx[k]
+
+    def emit(self, outputs, out_names):
+        live = set()
+        stack = [o for o in outputs if S.is_sym(o)]
+        while stack:
+            n = stack.pop()
+            if n.id in live:
+                continue
+            live.add(n.id)
+            for a in n.args:
+                if S.is_sym(a) and a.id not in live:
+                    stack.append(a)
+        R = self.real
+        L = self.lines
+        li = S.Tracer.lookup_index
+        cnt = {}
+        for n in S.G.nodes:
+            if n.id not in live or n.op == 'const':
+                continue
+            cnt[n.op] = cnt.get(n.op, 0) + 1
+            a = n.args
+            v = 'v%d' % n.id
+            op = n.op
+            r = self.ref
+            if op == 'X':
+                L.append('const %s %s = X[%d];' % (R, v, a[0]))
+            elif op == 'U':
+                L.append('const %s %s = U[%d];' % (R, v, a[0]))
+            elif op in ('add', 'sub', 'mul', 'div'):
+                sym = {'add': '+', 'sub': '-', 'mul': '*', 'div': '/'}[op]
+                L.append('const %s %s = %s %s %s;' % (R, v, r(a[0]), sym, r(a[1])))
+            elif op == 'sqrt':
+                L.append('const %s %s = PLANT_SQRT(%s);' % (R, v, r(a[0])))
+            elif op == 'max':
+                L.append('const %s %s = (%s > %s) ? %s : %s;' % (R, v, r(a[0]), r(a[1]), r(a[0]), r(a[1])))
+            elif op == 'min':
+                L.append('const %s %s = (%s < %s) ? %s : %s;' % (R, v, r(a[0]), r(a[1]), r(a[0]), r(a[1])))
+            elif op == 'neg':
+                L.append('const %s %s = -%s;' % (R, v, r(a[0])))
+            elif op == 'abs':
+                L.append('const %s %s = PLANT_FABS(%s);' % (R, v, r(a[0])))
+            elif op in ('cmp', 'cmpmask'):
+                sym = {'gt': '>', 'ge': '>=', 'lt': '<', 'le': '<=', 'eq': '==', 'ne': '!='}[a[0]]
+                L.append('const bool %s = %s %s %s;' % (v, r(a[1]), sym, r(a[2])))
+            elif op == 'select':
+                L.append('const %s %s = %s ? %s : %s;' % (R, v, r(a[0]), r(a[1]), r(a[2])))
+            elif op == 'mand':
+                L.append('const %s %s = %s ? %s : 0.0;' % (R, v, r(a[0]), r(a[1])))
+            elif op == 'mandn':
+                L.append('const %s %s = %s ? 0.0 : %s;' % (R, v, r(a[0]), r(a[1])))
+            elif op in ('sin', 'cos', 'tan', 'exp', 'log10'):
+                L.append('const %s %s = PLANT_%s(%s);' % (R, v, op.upper(), r(a[0])))
+            elif op == 'pow':
+                L.append('const %s %s = PLANT_POW(%s, %s);' % (R, v, r(a[0]), r(a[1])))
+            elif op == 'powsnf':
+                if a[1].op == 'const' and S.fval(a[1].args[0]) == 2.0:
+                    L.append('const %s %s = %s * %s;' % (R, v, r(a[0]), r(a[0])))     # rt_powd_snf(x, 2) == x*x
+                else:
+                    L.append('const %s %s = plant_powd_snf(%s, %s);' % (R, v, r(a[0]), r(a[1])))
+            elif op == 'lookup1':
+                kx, ky, u = a
+                xs, ys = self.tr.tables[kx], self.tr.tables[ky]
+                iv, dv = self.index_of(kx, u)
+                sl = [(ys[i + 1] - ys[i]) / (xs[i + 1] - xs[i]) for i in range(len(xs) - 1)]
+                sn = self.derived('sl', sl)
+                yn = self.table(ky)
+                L.append('const %s %s = PLANT_TAB(%s)[%s] * %s + PLANT_TAB(%s)[%s];' % (R, v, sn, iv, dv, yn, iv))
+            elif op == 'lookup2':
+                kx, ky, kz, x, y = a
+                xs, ys, zs = self.tr.tables[kx], self.tr.tables[ky], self.tr.tables[kz]
+                nx, ny = len(xs), len(ys)
+                if x.op == 'const':
+                    xv = S.fval(x.args[0])
+                    ix = li(xs, xv)
+                    dx = xs[ix + 1] - xs[ix]
+                    ux = xv - xs[ix]
+                    col = [(zs[ix + 1 + nx * j] - zs[ix + nx * j]) / dx * ux + zs[ix + nx * j] for j in range(ny)]
+                    sa = [(col[j + 1] - col[j]) / (ys[j + 1] - ys[j]) for j in range(ny - 1)]
+                    an = self.derived('col', col)
+                    sn = self.derived('sa', sa)
+                    iv, dv = self.index_of(ky, y)
+                    L.append('const %s %s = PLANT_TAB(%s)[%s] * %s + PLANT_TAB(%s)[%s];' % (R, v, sn, iv, dv, an, iv))
+                    cnt['lookup2->1'] = cnt.get('lookup2->1', 0) + 1
+                else:
+                    sx = []
+                    for j in range(ny):
+                        for i in range(nx):
+                            sx.append((zs[i + 1 + nx * j] - zs[i + nx * j]) / (xs[i + 1] - xs[i]) if i < nx - 1 else 0.0)
+                    dy = [ys[j + 1] - ys[j] for j in range(ny - 1)]
+                    sxn = self.derived('sx', sx)
+                    dyn = self.derived('dy', dy)
+                    zn = self.table(kz)
+                    ixv, dxv = self.index_of(kx, x)
+                    if y.op == 'const':
+                        raise NotImplementedError('lookup2 with constant y')
+                    iyv, dyv = self.index_of(ky, y)
+                    L.append('const int k%d = %s + %d * %s;' % (n.id, ixv, nx, iyv))
+                    L.append('const %s a%d = PLANT_TAB(%s)[k%d] * %s + PLANT_TAB(%s)[k%d];' % (R, n.id, sxn, n.id, dxv, zn, n.id))
+                    L.append('const %s b%d = PLANT_TAB(%s)[k%d + %d] * %s + PLANT_TAB(%s)[k%d + %d];' % (R, n.id, sxn, n.id, nx, dxv, zn, n.id, nx))
+                    L.append('const %s %s = (b%d - a%d) / PLANT_TAB(%s)[%s] * %s + a%d;' % (R, v, n.id, n.id, dyn, iyv, dyv, n.id))
+            elif op == 'table3':
+                k1, k2, k3, k4, u0, u1, u2 = a
+                t = [self.table(k) for k in (k1, k2, k3, k4)]
+                ns = [len(self.tabs[x]) for x in t[:3]]
+                L.append('const %s %s = plant_table3(PLANT_TAB(%s), %d, PLANT_TAB(%s), %d, PLANT_TAB(%s), %d, PLANT_TAB(%s), %s, %s, %s);'
+                         % (R, v, t[0], ns[0], t[1], ns[1], t[2], ns[2], t[3], r(u0), r(u1), r(u2)))
+            else:
+                raise NotImplementedError(op)
+        for o, name in zip(outputs, out_names):
+            L.append('%s = %s;' % (name, self.ref(o)))
+        self.stats = cnt
+        return cnt
+
+    def tables_text(self):
+        out = []
+        used = set()
+        body = '\n'.join(self.lines)
+        for name, vals in self.tabs.items():
+            if ('(%s)' % name) not in body:
+                continue
+            used.add(name)
+            out.append('PLANT_TABLE(%s, %d) = {' % (name, len(vals)))
+            for i in range(0, len(vals), 4):
+                out.append('  ' + ', '.join(hexf(x) for x in vals[i:i + 4]) + ',')
+            out.append('};')
+        self.table_bytes = sum(8 * len(self.tabs[n]) for n in used)
+        return '\n'.join(out)
+
+    def body_text(self):
+        return '\n'.join(self.lines)
