@@ -1,0 +1,295 @@
+#!/usr/bin/env python
+"""Benchmark of the per-generation fitness hot path (BASELINE.json metric: env-steps/s).
+
+    python bench.py --gpus N --steps K --warmup W            our arm (CUDA, one rank per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...  reference arm: the reference's CPU path (native plant
+                                                             binary + batch-1 torch actor + numpy wrapper) on host cores
+
+A "step" = one population evaluation (one generation's rollouts): pop x envs trajectories of up to 2001 plant steps.
+Workload = BASELINE.json configs[2]: PH-LAB nominal h2000_v90, pop=512, 128 envs, 2001-step horizon, actor h=72 L=3 tanh.
+The population is the shipped SERL10 checkpoint tiled to pop with N(0,1e-3) weight noise (trained actors fly the full
+horizon; SURVEY.md 8(d) mode ii); executed steps are counted from the kernel's own step counters, not assumed.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+POP, N_ENVS, HORIZON, HIDDEN = 512, 128, 2001, 72
+BYTES_PER_STEP = 208.0          # state round-trip model, the HBM denominator BASELINE.md asks for
+FLOP_PER_STEP_F64 = 6 * 900.0   # generated RHS: ~700 fp64 flops + ~65 table interpolations per stage, 6 stages
+FLOP_PER_STEP_F32 = 34600.0     # actor h=72 L=3
+
+
+def population(pop, seed=7):
+    acts = np.load(os.path.join(ROOT, 'tests', 'golden', 'actors.npz'))
+    base = acts['serl10_pop_h72_tanh']
+    rng = np.random.RandomState(seed)
+    w = base[np.arange(pop) % base.shape[0]].astype(np.float32)
+    w = w + rng.normal(0, 1e-3, size=w.shape).astype(np.float32)
+    return np.ascontiguousarray(w)
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get('hbm_gbs', 6650.0), 'measured'
+    return 6650.0, 'fallback'
+
+
+class ClockSampler:
+    def __init__(self, idx):
+        self.p = None
+        self.path = '/tmp/serl_clocks_%d.csv' % os.getpid()
+        try:
+            self.p = subprocess.Popen(
+                ['nvidia-smi', '-i', str(idx), '--query-gpu=clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+                 'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+                 'clocks_event_reasons.sw_power_cap', '--format=csv,noheader,nounits', '-lms', '200'],
+                stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(',')]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[4:8]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        if sm:
+            out = {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(mx)), 'reasons': sorted(reasons), 'samples': len(sm)}
+        return out
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def _cpu_worker(args):
+    import torch
+    torch.set_num_threads(1)
+    from oracle import actor as A, phlab
+    w, jobs, lv, st = args
+    env = phlab.CitationEnv('nominal', 'auto')
+    steps = 0
+    t0 = time.perf_counter()
+    for a, e in jobs:
+        act = A.unflatten(w[a], hidden=HIDDEN)
+        steps += phlab.run_episode(env, act, lv[e], st[e])['steps']
+    return steps, time.perf_counter() - t0
+
+
+def cpu_reference_throughput(n_episodes_per_core=1, cores=None):
+    """The reference's CPU execution model (one process per core, each with its own copy of the native plant binary,
+    batch-1 torch forward, numpy wrapper) on a bounded sample of the bench workload."""
+    import multiprocessing as mp
+    from oracle import refsig, build as ob
+    ob.build()
+    cores = cores or os.cpu_count()
+    w = population(8)
+    lv, st = refsig.make_ref_params(8)
+    jobs = [[((c * n_episodes_per_core + i) % 8, (c + i) % 8) for i in range(n_episodes_per_core)] for c in range(cores)]
+    ctx = mp.get_context('spawn')
+    t0 = time.perf_counter()
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_cpu_worker, [(w, j, lv, st) for j in jobs])
+    wall = time.perf_counter() - t0
+    steps = sum(r[0] for r in res)
+    busy = max(r[1] for r in res)
+    return steps / busy, steps, cores, wall, ('reference' if ob.have_ref() else 'port')
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    vals = []
+    kind = 'port'
+    for i in range(args.warmup + args.steps):
+        v, steps, cores, wall, kind = cpu_reference_throughput(n_episodes_per_core=1)
+        if i >= args.warmup:
+            vals.append((v, steps, wall))
+    v = float(np.mean([x[0] for x in vals]))
+    sample = '%d cores x 1 episode (<=2001 steps) of the pop=512 x 128-env workload per step' % cores
+    line = {
+        'impl': 'reference', 'metric': 'env_steps_per_sec', 'value': v, 'unit': 'env-steps/s', 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': 1e3 * float(np.mean([x[2] for x in vals])), 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': 'PH-LAB nominal h2000_v90, pop=512, 128 envs, 2001-step horizon, actor h=72 L=3 tanh (bounded sample)'},
+        'cpu_baseline': {'value': v, 'unit': 'env-steps/s', 'cores': cores, 'kind': kind, 'sample': sample},
+        'e2e': {'value': v, 'unit': 'env-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from serl_b200 import rollout, _native
+    from serl_b200 import refsig
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device (the product path has no CPU fallback)')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    sh = rollout.actor_shape(HIDDEN, 3, 'tanh')
+    w_host = torch.from_numpy(population(POP, seed=7 + rank)).pin_memory()
+    lv_np, st_np = refsig.make_ref_params(N_ENVS)
+    lv_host = torch.from_numpy(lv_np).pin_memory()
+    st_host = torch.from_numpy(st_np).pin_memory()
+    md_host = torch.full((N_ENVS,), rollout.mode_code('nominal'), dtype=torch.int32).pin_memory()
+    w = w_host.to(dev)
+    lv, st, md = lv_host.to(dev), st_host.to(dev), md_host.to(dev)
+    fit_all = torch.empty((world * POP,), dtype=torch.float64, device=dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def one_step(res=None):
+        r = rollout.population_rollout(w, sh, lv, st, md, horizon=HORIZON, out=res)
+        if world > 1:
+            dist.all_gather_into_tensor(fit_all, r.fitness)
+        else:
+            fit_all.copy_(r.fitness)
+        return r
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    res = None
+    for _ in range(args.warmup):
+        flush.zero_()
+        res = one_step(res)
+    sync_all()
+    launches0 = _native.lib().serl_launch_count()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_begin = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    sync_all()
+    t_begin.record()
+    for i in range(args.steps):
+        flush.zero_()
+        ev[i][0].record()
+        res = one_step(res)
+        ev[i][1].record()
+    t_end.record()
+    sync_all()
+    clocks = sampler.stop() if sampler else None
+    launches = _native.lib().serl_launch_count() - launches0
+    elapsed_ms = t_begin.elapsed_time(t_end)
+    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    local_steps = int(res.steps.sum().item())
+    stats = torch.tensor([elapsed_ms, kern_ms], dtype=torch.float64, device=dev)
+    tot = torch.tensor([float(local_steps)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    elapsed_ms, kern_ms = stats.tolist()
+    total_steps = tot.item()
+    value = total_steps * args.steps / (elapsed_ms * 1e-3)
+
+    # ---- end to end through the public API with host buffers (H2D genomes + env params, D2H fitness) every step
+    fit_host = torch.empty((POP,), dtype=torch.float64).pin_memory()
+    h2d = w_host.numel() * 4 + lv_host.numel() * 8 + st_host.numel() * 8 + md_host.numel() * 4
+    d2h = fit_host.numel() * 8
+
+    def e2e_step(res):
+        w.copy_(w_host, non_blocking=True)
+        lv.copy_(lv_host, non_blocking=True)
+        st.copy_(st_host, non_blocking=True)
+        md.copy_(md_host, non_blocking=True)
+        r = one_step(res)
+        fit_host.copy_(r.fitness, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return r
+
+    res = e2e_step(res)
+    sync_all()
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    n_e2e = max(1, min(args.steps, 3))
+    for _ in range(n_e2e):
+        res = e2e_step(res)
+    t1.record()
+    sync_all()
+    e2e_ms = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_value = total_steps * n_e2e / (e2e_ms.item() * 1e-3)
+
+    if rank == 0:
+        peak, how = peaks()
+        per_gpu_steps = total_steps / world
+        achieved = BYTES_PER_STEP * per_gpu_steps / (kern_ms * 1e-3) / 1e9
+        line = {
+            'metric': 'env_steps_per_sec', 'value': value, 'unit': 'env-steps/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': elapsed_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f64 plant + f32 actor', 'data': 'synthetic',
+            'config': {'workload': 'PH-LAB nominal h2000_v90, pop=512/GPU, 128 envs, 2001-step horizon, actor h=72 L=3 tanh; '
+                                   'SERL10 checkpoint tiled + N(0,1e-3) noise; executed steps counted by the kernel',
+                       'pop_per_gpu': POP, 'n_envs': N_ENVS, 'horizon': HORIZON, 'hidden': HIDDEN,
+                       'executed_steps_per_step': total_steps, 'l2': 'flushed between timed iterations (256 MiB memset)',
+                       'parallelism': 'population sharded over %d GPU(s), NCCL all-gather of fitness' % world},
+            'clocks': clocks,
+            'e2e': {'value': e2e_value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
+            'gpu_launches': int(launches),
+            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
+                         'peak_source': how, 'kernel': 'rollout_kernel', 'kernel_ms': kern_ms,
+                         'note': 'BASELINE metric denominator (208 B/env-step state round-trip model); the kernel keeps state on chip and is '
+                                 'bound by fp64/fp32 issue, see fp_issue',
+                         'fp_issue': {'f64_gflops': FLOP_PER_STEP_F64 * per_gpu_steps / (kern_ms * 1e-3) / 1e9,
+                                      'f32_gflops': FLOP_PER_STEP_F32 * per_gpu_steps / (kern_ms * 1e-3) / 1e9}},
+        }
+        if world == 1 and not args.no_cpu:
+            v, steps, cores, wall, kind = cpu_reference_throughput(n_episodes_per_core=1)
+            line['cpu_baseline'] = {'value': v, 'unit': 'env-steps/s', 'cores': cores, 'kind': kind,
+                                    'sample': '%d cores x 1 episode (%d env-steps total) of the same workload, one process per core' % (cores, steps)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,80 @@
+/* serl_b200 — C-ABI of the B200-native population-rollout + neuro-evolution engine.
+ *
+ * Drop-in boundary for the per-generation fitness hot path of VladGavra98/SERL (paths relative to the
+ * reference tree).  All pointers named d_* are DEVICE pointers owned by the caller; `stream` is a
+ * cudaStream_t passed as void* (NULL = default stream).  Every entry point returns 0 on success or a
+ * negative serl_status; serl_last_error() gives the message of the last failure on the calling thread.
+ * There is no CPU fallback: without a CUDA device every compute entry point fails with SERL_ERR_CUDA.
+ */
+#ifndef SERL_B200_H
+#define SERL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    SERL_OK = 0,
+    SERL_ERR_ARG = -1,      /* bad argument (unsupported hidden size, null pointer, ...) */
+    SERL_ERR_CUDA = -2,     /* CUDA runtime error / no device */
+    SERL_ERR_UNSUPPORTED = -3
+} serl_status;
+
+/* activation ids: base/core/mod_utils.py:14-18 ('relu' is LeakyReLU(0.01) in the reference) */
+enum { SERL_ACT_TANH = 0, SERL_ACT_ELU = 1, SERL_ACT_LEAKY_RELU = 2 };
+
+/* plant variants = the reference's distinct native builds envs/<variant>/_citation*.so */
+enum { SERL_PLANT_H2000_V90 = 0, SERL_PLANT_ICE = 1, SERL_PLANT_CG = 2, SERL_PLANT_CG_FOR = 3,
+       SERL_PLANT_H2000_V150 = 4, SERL_PLANT_H10000_V90 = 5, SERL_PLANT_COUNT = 6 };
+/* command faults = envs/{be,jr,sa,se}/citation.py:71-79; env_mode = variant | (fault << 8) */
+enum { SERL_FAULT_NONE = 0, SERL_FAULT_BE = 1, SERL_FAULT_JR = 2, SERL_FAULT_SA = 3, SERL_FAULT_SE = 4 };
+
+#define SERL_REF_BLOCKS 6   /* reference-signal blocks per channel (oracle/refsig.py) */
+
+/* Actor shape: base/core/genetic_agent.py:69-101.  Genome layout = order of nn.Module.parameters(). */
+typedef struct {
+    int32_t state_dim;    /* 7  (envs/phlabenv.py:92-93,220: 3 tracking errors + p,q,r,alpha) */
+    int32_t action_dim;   /* 3 */
+    int32_t hidden;       /* h */
+    int32_t num_layers;   /* L hidden [Linear,LayerNorm,act] blocks */
+    int32_t activation;   /* SERL_ACT_* */
+} serl_actor_shape;
+
+/* number of fp32 parameters of one actor: S*h+h + L*(h*h+3h) + h*A+A */
+int64_t serl_actor_num_params(const serl_actor_shape* shape);
+
+/* Population rollout — replaces the loop `for net in pop: for i in range(num_evals): evaluate(net)` of
+ * base/core/agent.py:234-241 with Agent.evaluate (agent.py:63-138), CitationEnv.reset/step
+ * (envs/phlabenv.py:401-482), Actor.select_action (genetic_agent.py:107-109) and the native plant
+ * step (envs/<variant>/_citation*.so: step @0x6030) fused in one kernel.
+ *
+ *   d_weights   [pop, P] fp32, row = one actor genome
+ *   d_ref_levels[n_envs, 2, SERL_REF_BLOCKS] f64 (deg), d_ref_starts same shape (s)
+ *   d_env_mode  [n_envs] int32, variant | fault << 8
+ *   horizon     max steps per episode (reference: 2001, phlabenv.py:82,181,392)
+ * outputs
+ *   d_returns   [pop, n_envs] f64  sum of rewards (agent.py:129)
+ *   d_steps     [pop, n_envs] int32 executed steps
+ *   d_fitness   [pop] f64 mean over envs (agent.py:245), may be NULL
+ * optional single-trajectory traces (each may be NULL), layout [pop, n_envs, horizon, k]:
+ *   d_trace_x (k=12, state before each step; psi/x_e/y_e are integrated only when tracing),
+ *   d_trace_u (k=3, commanded deflection last_u), d_trace_r (k=1, reward)
+ */
+int serl_rollout(const float* d_weights, int32_t pop, const serl_actor_shape* shape,
+                 const double* d_ref_levels, const double* d_ref_starts, const int32_t* d_env_mode,
+                 int32_t n_envs, int32_t horizon,
+                 double* d_returns, int32_t* d_steps, double* d_fitness,
+                 double* d_trace_x, double* d_trace_u, double* d_trace_r,
+                 void* stream);
+
+/* number of kernels serl_* entry points have launched so far in this process (bench bookkeeping) */
+int64_t serl_launch_count(void);
+
+const char* serl_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,44 @@
+"""ctypes binding of the C-ABI library (include/serl_b200.h).  The product path has no CPU fallback:
+importing succeeds without a GPU (so host logic is testable), but the library must exist and every
+compute call fails loudly when CUDA is unavailable."""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'libserl_b200.so')
+
+
+class ActorShape(ctypes.Structure):
+    _fields_ = [('state_dim', ctypes.c_int32), ('action_dim', ctypes.c_int32), ('hidden', ctypes.c_int32),
+                ('num_layers', ctypes.c_int32), ('activation', ctypes.c_int32)]
+
+
+ACTIVATIONS = {'tanh': 0, 'elu': 1, 'relu': 2}
+_lib = None
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NativeError('serl_b200: %s is missing — build it with `python -m serl_b200.build` '
+                              '(there is no CPU fallback)' % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        vp, i32, i64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64
+        L.serl_actor_num_params.restype = i64
+        L.serl_actor_num_params.argtypes = [ctypes.POINTER(ActorShape)]
+        L.serl_rollout.restype = ctypes.c_int
+        L.serl_rollout.argtypes = [vp, i32, ctypes.POINTER(ActorShape), vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp]
+        L.serl_launch_count.restype = i64
+        L.serl_last_error.restype = ctypes.c_char_p
+        _lib = L
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        raise NativeError('%s failed (%d): %s' % (what, rc, lib().serl_last_error().decode()))

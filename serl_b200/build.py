@@ -1,0 +1,54 @@
+"""Compile the CUDA extension (C-ABI shared library) for sm_100a, in-tree.
+
+    python -m serl_b200.build          -> serl_b200/libserl_b200.so
+nvcc cross-compiles without a GPU; the .so travels to the GPU box with the repo snapshot.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, 'csrc')
+LIB = os.path.join(HERE, 'libserl_b200.so')
+SOURCES = ['common.cu', 'rollout.cu']
+NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
+              '-Xcompiler', '-fPIC', '-Xptxas', '-v', '--fmad=false']
+
+
+def _deps():
+    out = []
+    for root, _, files in os.walk(CSRC):
+        out += [os.path.join(root, f) for f in files]
+    out.append(os.path.join(HERE, '..', 'include', 'serl_b200.h'))
+    return out
+
+
+def build(force=False, verbose=False):
+    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= max(os.path.getmtime(d) for d in _deps()):
+        return LIB
+    nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+    objs = []
+    os.makedirs(os.path.join(HERE, 'build'), exist_ok=True)
+    log = []
+    for src in SOURCES:
+        obj = os.path.join(HERE, 'build', src.replace('.cu', '.o'))
+        cmd = [nvcc] + NVCC_FLAGS + ['-c', os.path.join(CSRC, src), '-o', obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        log.append(r.stderr)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError('nvcc failed on ' + src)
+        objs.append(obj)
+    r = subprocess.run([nvcc, '-shared', '-o', LIB] + objs + ['-lcudart'], capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError('link failed')
+    with open(os.path.join(HERE, 'build', 'ptxas.log'), 'w') as f:
+        f.write('\n'.join(log))
+    if verbose:
+        print('\n'.join(log))
+    return LIB
+
+
+if __name__ == '__main__':
+    print(build(force=True, verbose='-v' in sys.argv))

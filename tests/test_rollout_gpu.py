@@ -1,0 +1,112 @@
+"""Parity of the CUDA rollout (through the C-ABI) against the oracle: same genomes, same reference signals,
+same fault modes.  Bar (BASELINE.json): termination step identical, episodic return within 1e-4 relative."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import actor as A, phlab, plant as P, refsig
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), 'golden')
+ACT = np.load(os.path.join(G, 'actors.npz'))
+REL_TOL = 1e-4
+
+
+def gpu_rollout(weights, hidden, activation, levels, starts, modes, trace=False, horizon=2001):
+    from serl_b200 import rollout
+    dev = torch.device('cuda:0')
+    sh = rollout.actor_shape(hidden, 3, activation)
+    w = torch.as_tensor(np.ascontiguousarray(weights, dtype=np.float32), device=dev)
+    lv = torch.as_tensor(levels, device=dev)
+    st = torch.as_tensor(starts, device=dev)
+    md = torch.as_tensor(np.array([rollout.mode_code(m) for m in modes], dtype=np.int32), device=dev)
+    r = rollout.population_rollout(w, sh, lv, st, md, horizon=horizon, trace=trace)
+    torch.cuda.synchronize()
+    return r
+
+
+def oracle_rollout(weights, hidden, activation, levels, starts, modes, record=False):
+    envs = {}
+    out = []
+    for a in range(weights.shape[0]):
+        act = A.unflatten(weights[a], hidden=hidden, activation=activation)
+        row = []
+        for e, m in enumerate(modes):
+            if m not in envs:
+                envs[m] = phlab.CitationEnv(m, 'auto')
+            row.append(phlab.run_episode(envs[m], act, levels[e], starts[e], record=record))
+        out.append(row)
+    return out
+
+
+def check(r, orc):
+    ret = r.returns.cpu().numpy()
+    stp = r.steps.cpu().numpy()
+    for a, row in enumerate(orc):
+        for e, o in enumerate(row):
+            assert stp[a, e] == o['steps'], (a, e, stp[a, e], o['steps'])
+            assert abs(ret[a, e] - o['fitness']) <= REL_TOL * abs(o['fitness']), (a, e, ret[a, e], o['fitness'])
+    fit = r.fitness.cpu().numpy()
+    ofit = np.array([np.mean([o['fitness'] for o in row]) for row in orc])
+    assert np.allclose(fit, ofit, rtol=REL_TOL, atol=0)
+
+
+def test_trained_population_nominal():
+    w = ACT['serl10_pop_h72_tanh'][:4]
+    lv, st = refsig.make_ref_params(3)
+    modes = ['nominal'] * 3
+    check(gpu_rollout(w, 72, 'tanh', lv, st, modes), oracle_rollout(w, 72, 'tanh', lv, st, modes))
+
+
+def test_random_init_population_terminates_early_like_oracle():
+    torch.manual_seed(7)
+    w = np.stack([A.flatten(A.Actor(hidden=72)) for _ in range(6)])
+    lv, st = refsig.make_ref_params(2, seed_base=123)
+    modes = ['nominal'] * 2
+    orc = oracle_rollout(w, 72, 'tanh', lv, st, modes)
+    assert any(o['steps'] < 2001 for row in orc for o in row)      # the case the test is about
+    check(gpu_rollout(w, 72, 'tanh', lv, st, modes), orc)
+
+
+def test_fault_modes_and_plant_variants():
+    w = ACT['serl10_pop_h72_tanh'][[0, 5]]
+    modes = ['be', 'jr', 'sa', 'se', 'ice', 'cg', 'cg-for', 'h2000-v150', 'h10000-v90']
+    lv, st = refsig.make_ref_params(len(modes), seed_base=99)
+    check(gpu_rollout(w, 72, 'tanh', lv, st, modes), oracle_rollout(w, 72, 'tanh', lv, st, modes))
+
+
+def test_other_actor_shapes():
+    lv, st = refsig.make_ref_params(2, seed_base=5)
+    modes = ['nominal', 'nominal']
+    w = ACT['serl50_pop8_h32_tanh'][:3]
+    check(gpu_rollout(w, 32, 'tanh', lv, st, modes), oracle_rollout(w, 32, 'tanh', lv, st, modes))
+    w = ACT['td3_h96_relu'][None]
+    check(gpu_rollout(w, 96, 'relu', lv, st, modes), oracle_rollout(w, 96, 'relu', lv, st, modes))
+
+
+def test_trace_matches_oracle_trajectory():
+    w = ACT['serl10_elite_h72_tanh'][None]
+    lv, st = refsig.make_ref_params(1, seed_base=31)
+    r = gpu_rollout(w, 72, 'tanh', lv, st, ['nominal'], trace=True)
+    o = oracle_rollout(w, 72, 'tanh', lv, st, ['nominal'], record=True)[0][0]
+    n = o['steps']
+    tx = r.trace_x[0, 0, :n].cpu().numpy()
+    live = [0, 1, 2, 3, 4, 5, 6, 7, 9]
+    assert np.abs(tx[:, live] - o['states'][:, live]).max() < 1e-4
+    assert np.abs(tx[:50, live] - o['states'][:50, live]).max() < 1e-6
+    assert np.abs(r.trace_u[0, 0, :n].cpu().numpy() - o['actions']).max() < 1e-4
+    assert np.abs(r.trace_r[0, 0, :n].cpu().numpy() - o['rewards']).max() < 1e-4
+
+
+def test_ragged_env_count_and_many_actors():
+    """n_envs not a multiple of the CTA size, more actors than SMs: every trajectory must be written."""
+    w = np.tile(ACT['serl50_pop8_h32_tanh'], (25, 1))          # 200 actors
+    lv, st = refsig.make_ref_params(130, seed_base=1000)
+    r = gpu_rollout(w, 32, 'tanh', lv, st, ['nominal'] * 130, horizon=60)
+    stp = r.steps.cpu().numpy()
+    ret = r.returns.cpu().numpy()
+    assert (stp == 60).all() and np.isfinite(ret).all()
+    # identical genomes x identical envs -> identical returns (determinism across CTAs)
+    assert np.array_equal(ret[:8], ret[8:16])

@@ -20,6 +20,17 @@ def hexf(x):
     return float(x).hex()
 
 
+def tables_text(tabs):
+    out = []
+    for name in sorted(tabs):
+        vals = tabs[name]
+        out.append('PLANT_TABLE(%s, %d) = {' % (name, len(vals)))
+        for i in range(0, len(vals), 4):
+            out.append('  ' + ', '.join(hexf(x) for x in vals[i:i + 4]) + ',')
+        out.append('};')
+    return '\n'.join(out)
+
+
 class Emitter:
     def __init__(self, tracer, real='real'):
         self.tr = tracer
@@ -31,17 +42,24 @@ class Emitter:
         self.stats = {}
 
     # ---- tables ----
+    @staticmethod
+    def _hname(prefix, vals):
+        import hashlib, struct
+        h = hashlib.md5(struct.pack('<%dd' % len(vals), *vals)).hexdigest()[:10]
+        return '%s%d_%s' % (prefix, len(vals), h)
+
     def table(self, key, prefix='T'):
         if key not in self.tabname:
-            name = '%s%d' % (prefix, len(self.tabname))
+            vals = list(self.tr.tables[key])
+            name = self._hname(prefix, vals)
             self.tabname[key] = name
-            self.tabs[name] = list(self.tr.tables[key]) if key in self.tr.tables else list(key[1])
+            self.tabs[name] = vals
         return self.tabname[key]
 
     def derived(self, tag, vals):
         key = ('derived', tuple(vals), tag)
         if key not in self.tabname:
-            name = 'D%d' % len(self.tabname)
+            name = self._hname('D', list(vals))
             self.tabname[key] = name
             self.tabs[name] = list(vals)
         return self.tabname[key]
@@ -178,20 +196,14 @@ class Emitter:
         self.stats = cnt
         return cnt
 
-    def tables_text(self):
-        out = []
-        used = set()
+    def used_tables(self):
         body = '\n'.join(self.lines)
-        for name, vals in self.tabs.items():
-            if ('(%s)' % name) not in body:
-                continue
-            used.add(name)
-            out.append('PLANT_TABLE(%s, %d) = {' % (name, len(vals)))
-            for i in range(0, len(vals), 4):
-                out.append('  ' + ', '.join(hexf(x) for x in vals[i:i + 4]) + ',')
-            out.append('};')
-        self.table_bytes = sum(8 * len(self.tabs[n]) for n in used)
-        return '\n'.join(out)
+        return {name: vals for name, vals in self.tabs.items() if ('(%s)' % name) in body}
+
+    def tables_text(self):
+        used = self.used_tables()
+        self.table_bytes = sum(8 * len(v) for v in used.values())
+        return tables_text(used)
 
     def body_text(self):
         return '\n'.join(self.lines)

@@ -218,7 +218,8 @@ def split_ops(s):
 class Image:
     def __init__(self, so_path, workdir):
         os.makedirs(workdir, exist_ok=True)
-        self.path = os.path.join(workdir, 'plant_' + re.sub(r'\W', '_', os.path.dirname(so_path)[-20:]) + '.so')
+        Image._n = getattr(Image, '_n', 0) + 1      # a fresh copy per load: never overwrite a mapped file
+        self.path = os.path.join(workdir, 'plant_%d_%d_' % (os.getpid(), Image._n) + re.sub(r'\W', '_', os.path.dirname(so_path)[-20:]) + '.so')
         shutil.copy(so_path, self.path)
         os.chmod(self.path, 0o755)
         self.lib = ctypes.CDLL(self.path)
