@@ -69,6 +69,30 @@ int serl_rollout(const float* d_weights, int32_t pop, const serl_actor_shape* sh
                  double* d_trace_x, double* d_trace_u, double* d_trace_r,
                  void* stream);
 
+/* ---- neuro-evolution (base/core/mod_neuro_evo.py, classic operators) -------------------------------------
+ * All random draws are made on the host in the reference's order; the device applies compact op lists.
+ * Launches issued on one stream execute in order; a caller must put ops with a write-after-write or
+ * read-after-write hazard on the same genome into separate launches (serl_b200/evo.py does). */
+
+/* K2: index_rank = argsort(fitness)[::-1] (mod_neuro_evo.py:460; ties -> larger index first, NaN first) and the
+ * tournament winners offsprings_raw[s] = index_rank[min(draws[s,0..2])] (:44-47). d_draws: [n_off,3] int32. */
+int serl_ssne_select(const double* d_fitness, int32_t pop, const int32_t* d_draws, int32_t n_off,
+                     int32_t* d_index_rank, int32_t* d_offsprings_raw, void* stream);
+
+/* K3: SSNE.clone (:371-376) for n (src,dst) genome pairs, d_pairs [n,2]. */
+int serl_ssne_clone(float* d_weights, int32_t pop, int32_t P, const int32_t* d_pairs, int32_t n, void* stream);
+
+/* K4: per pair {g1,g2,src1,src2,op_begin,op_count} (d_pair_desc [n_pairs,6]): clone src1->g1, src2->g2 (:519-522)
+ * then crossover_inplace (:61-93) as ordered copies d_ops [.,3] = {offset,len,dir} (dir 0: g1<-g2, 1: g2<-g1). */
+int serl_ssne_crossover(float* d_weights, int32_t pop, int32_t P, const int32_t* d_pair_desc, int32_t n_pairs,
+                        const int32_t* d_ops, void* stream);
+
+/* K5: mutate_inplace (:329-369): d_seg [n_seg,3] = {actor, op_begin, op_count}; op k: element d_op_off[k],
+ * d_op_kind[k] (0 normal, 1 super, 2 reset), standard-normal draw d_op_z[k] already rounded to fp32. */
+int serl_ssne_mutate(float* d_weights, int32_t pop, int32_t P, const int32_t* d_seg, int32_t n_seg,
+                     const int32_t* d_op_off, const int32_t* d_op_kind, const float* d_op_z,
+                     float mag32, float super32, void* stream);
+
 /* number of kernels serl_* entry points have launched so far in this process (bench bookkeeping) */
 int64_t serl_launch_count(void);
 
