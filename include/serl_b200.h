@@ -54,19 +54,21 @@ int64_t serl_actor_num_params(const serl_actor_shape* shape);
  *   d_ref_levels[n_envs, 2, SERL_REF_BLOCKS] f64 (deg), d_ref_starts same shape (s)
  *   d_env_mode  [n_envs] int32, variant | fault << 8
  *   horizon     max steps per episode (reference: 2001, phlabenv.py:82,181,392)
+ *   d_action_noise optional [pop, n_envs, horizon, 3] fp32: clipped exploration noise added to the policy output
+ *               (base/core/agent.py:90-93, is_action_noise=True); NULL for fitness evaluation
  * outputs
  *   d_returns   [pop, n_envs] f64  sum of rewards (agent.py:129)
  *   d_steps     [pop, n_envs] int32 executed steps
  *   d_fitness   [pop] f64 mean over envs (agent.py:245), may be NULL
- * optional single-trajectory traces (each may be NULL), layout [pop, n_envs, horizon, k]:
- *   d_trace_x (k=12, state before each step; psi/x_e/y_e are integrated only when tracing),
- *   d_trace_u (k=3, commanded deflection last_u), d_trace_r (k=1, reward)
+ *   d_trace     optional [pop, n_envs, horizon, SERL_TRACE_COLS] f64 per-step record (Episode fields, core/utils.py:12-36):
+ *               0-11 state before the step (psi, x_e, y_e = NaN-free only in the full-state build),
+ *               12-14 commanded deflection last_u, 15 reward, 16-18 action fed to the env, 19-21 tracking error
  */
+#define SERL_TRACE_COLS 22
 int serl_rollout(const float* d_weights, int32_t pop, const serl_actor_shape* shape,
                  const double* d_ref_levels, const double* d_ref_starts, const int32_t* d_env_mode,
-                 int32_t n_envs, int32_t horizon,
-                 double* d_returns, int32_t* d_steps, double* d_fitness,
-                 double* d_trace_x, double* d_trace_u, double* d_trace_r,
+                 int32_t n_envs, int32_t horizon, const float* d_action_noise,
+                 double* d_returns, int32_t* d_steps, double* d_fitness, double* d_trace,
                  void* stream);
 
 /* ---- neuro-evolution (base/core/mod_neuro_evo.py, classic operators) -------------------------------------

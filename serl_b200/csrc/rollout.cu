@@ -1,14 +1,19 @@
 // K1 — fused population rollout for sm_100a.
 //
-// One thread = one (actor, env) trajectory; one CTA = one actor x up to ROLLOUT_THREADS envs, with that
-// actor's fp32 genome staged once in shared memory.  Per step the thread runs, entirely on chip:
-//   Actor.select_action  (base/core/genetic_agent.py:104-109; LayerNorm base/core/mod_utils.py:47-50)  fp32
+// One thread = one (actor, env) trajectory; one CTA = one actor x up to 128 envs, with that actor's fp32 genome
+// staged once in shared memory.  Per step the CTA runs, entirely on chip:
+//   Actor.select_action  (base/core/genetic_agent.py:104-109; LayerNorm base/core/mod_utils.py:47-50)        fp32
 //   CitationEnv.step     (envs/phlabenv.py:430-482: action scaling :62-73, fault shims envs/{be,jr,sa,se}/citation.py,
 //                         reward :362-367, termination + penalty :391-399)                                fp64
 //   native plant step    (envs/<variant>/_citation*.so step @0x6030: 6-stage Dormand-Prince ode5, h = 0.01, RHS
 //                         generated from the binary by tools/lift -> csrc/gen/plant_rhs_<variant>.h)          fp64
 // and accumulates the episodic return (base/core/agent.py:129).  HBM is touched only at episode start
-// (genome, reference-signal parameters) and end (return, step count) unless traces are requested.
+// (genome, reference-signal parameters) and end (return, step count) unless a trace is requested.
+//
+// Two actor implementations:
+//   rollout_kernel_gemm<H>  block-cooperative register-tiled GEMM: warp = 1/4 of the output neurons, lane = 4 envs;
+//                           weights transposed in smem, one activation buffer -> 2 CTAs/SM at h=72.  (h in {32,64,72,96})
+//   rollout_kernel_simple   every thread runs the whole MLP for its env (any h that fits); reference / fallback shape.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -45,8 +50,8 @@ typedef double real;
 #define ROLLOUT_THREADS 128
 #define NX 19
 
-// live continuous states of the plant: p q r V alpha beta phi theta | h | washout | N1 N1 N2 N2.
-// psi, x_e, y_e never feed back; Parameter_CSTATE(_g) have zero derivative and are folded into the RHS.
+// live continuous states of the plant: p q r V alpha beta phi theta | h | washout | N1 N1 N2 N2
+// (psi, x_e, y_e never feed back and are integrated only for traces; Parameter_CSTATE(_g) are folded constants).
 __device__ __forceinline__ void plant_rhs(int variant, const double* X, const double* U, double* xdot)
 {
     switch (variant) {
@@ -108,7 +113,7 @@ __device__ __forceinline__ float act_fn(int act, float x)
     return x > 0.f ? x : 0.01f * x;
 }
 
-// reference-signal value in degrees (oracle/refsig.py: ref_value_deg)
+// reference-signal value in degrees (serl_b200/refsig.py; recovered shape of signals.RandomizedCosineStepSequence)
 __device__ __forceinline__ double ref_deg(const double* lv, const double* st, double t, double offset)
 {
     int k = 0;
@@ -121,14 +126,124 @@ __device__ __forceinline__ double ref_deg(const double* lv, const double* st, do
     return offset + (lv[k - 1] + (lv[k] - lv[k - 1]) * (0.5 * (1.0 - cos(3.141592653589793 * x))));
 }
 
-// v1 actor forward: every thread evaluates the whole MLP for its own observation; weights are broadcast
-// reads from shared memory, activations live in a per-thread column of shared memory (conflict-free).
-__device__ void actor_forward(const float* __restrict__ w, const serl_actor_shape sh, float* bufA, float* bufB,
-                              int tid, int nthr, const float* obs, float* action)
+// ---- per-trajectory environment (CitationEnv restated for one thread) --------------------------------------
+struct RolloutArgs {
+    const float* weights; int P; serl_actor_shape sh;
+    const double* ref_levels; const double* ref_starts; const int* env_mode; int n_envs; int horizon;
+    const float* action_noise;      // optional [pop, n_envs, horizon, 3]: clipped exploration noise (agent.py:90-93)
+    double* returns; int* steps; double* trace;   // trace optional [pop, n_envs, horizon, SERL_TRACE_COLS]
+};
+
+struct Env {
+    double X[NX];
+    double lv[2][SERL_REF_BLOCKS], st[2][SERL_REF_BLOCKS];
+    double t, ret, theta_trim;
+    int variant, fault, k;
+    bool done;
+};
+
+#define DEG2RAD 0.017453292519943295   // numpy deg2rad multiplier (pi/180)
+#define RAD2DEG 57.29577951308232      // numpy rad2deg multiplier (180/pi)
+
+__device__ __forceinline__ void apply_fault(int fault, const double* u, double* c)
+{
+    c[0] = u[0]; c[1] = u[1]; c[2] = u[2];
+    if (fault == SERL_FAULT_BE) c[0] = u[0] * 0.3;                                       // envs/be/citation.py:71-75
+    else if (fault == SERL_FAULT_JR) c[2] = 15 * 3.14159 / 180;                          // envs/jr/citation.py:71-75
+    else if (fault == SERL_FAULT_SA) { const double b = 1.0 * DEG2RAD; c[1] = fmin(fmax(u[1], -b), b); }   // envs/sa :73-79
+    else if (fault == SERL_FAULT_SE) { const double b = 2.5 * DEG2RAD; c[0] = fmin(fmax(u[0], -b), b); }   // envs/se :73-79
+}
+
+// reset(): initialize(), one zero-command step returns the initial state (phlabenv.py:401-428). obs = [0,0,0,p,q,r,alpha]
+__device__ void env_reset(Env& e, const RolloutArgs& a, int env, float* obs)
+{
+    const int mode = a.env_mode[env];
+    e.variant = mode & 0xff;
+    e.fault = (mode >> 8) & 0xff;
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int j = 0; j < SERL_REF_BLOCKS; ++j) {
+            e.lv[c][j] = a.ref_levels[((size_t)env * 2 + c) * SERL_REF_BLOCKS + j];
+            e.st[c][j] = a.ref_starts[((size_t)env * 2 + c) * SERL_REF_BLOCKS + j];
+        }
+    const double* ic = plant_ic(e.variant);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) e.X[i] = ic[i];
+    obs[0] = obs[1] = obs[2] = 0.f;
+    obs[3] = (float)e.X[0]; obs[4] = (float)e.X[1]; obs[5] = (float)e.X[2]; obs[6] = (float)e.X[4];
+    e.theta_trim = e.X[7] * RAD2DEG;
+    double U[3] = {0.0, 0.0, 0.0}, cmd[3];
+    apply_fault(e.fault, U, cmd);
+    plant_step(e.variant, e.X, cmd);
+    e.t = 0.0; e.ret = 0.0; e.k = 0; e.done = false;
+}
+
+// one CitationEnv.step (phlabenv.py:430-482) + the bookkeeping of Agent.evaluate (agent.py:85-118)
+__device__ void env_step(Env& e, const RolloutArgs& ar, size_t traj, const float* a, float* obs)
+{
+    const double bound = 10.0 * DEG2RAD;                       // phlabenv.py:208
+    const double max_theta = 60.0 * DEG2RAD, max_phi = 75.0 * DEG2RAD;
+    const double k_err = 6.0 / 3.141592653589793;              // phlabenv.py:226-231
+    const double k_err4 = k_err * 4.0;
+    double U[3], cmd[3], act_d[3];
+    if (ar.action_noise) {
+        // action = clip(action + clipped_noise, -1, 1) in float64, then scale_action in float64 (agent.py:90-96)
+        const float* nz = ar.action_noise + (traj * ar.horizon + e.k) * 3;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            act_d[i] = fmin(fmax((double)a[i] + (double)nz[i], -1.0), 1.0);
+            U[i] = -bound + 0.5 * (act_d[i] + 1.0) * (bound - (-bound));
+        }
+    } else {
+        // scale_action: low + 0.5*(a + 1.0)*(high - low) with a float32: (a + 1.0) and the halving round in fp32 (:72-73)
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            act_d[i] = (double)a[i];
+            const float t1 = a[i] + 1.0f;
+            const float t2 = 0.5f * t1;
+            U[i] = -bound + (double)t2 * (bound - (-bound));
+        }
+    }
+    apply_fault(e.fault, U, cmd);
+    double xo[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) xo[i] = e.X[i];
+    plant_step(e.variant, e.X, cmd);
+
+    const double t = e.t;
+    const double r_th = ref_deg(e.lv[0], e.st[0], t, e.theta_trim) * DEG2RAD;
+    const double r_ph = ref_deg(e.lv[1], e.st[1], t, 0.0) * DEG2RAD;
+    const double e0 = r_th - xo[7], e1 = r_ph - xo[6], e2 = 0.0 - xo[5];
+    const double c0 = fabs(fmin(fmax(k_err * e0, -1.0), 1.0));
+    const double c1 = fabs(fmin(fmax(k_err * e1, -1.0), 1.0));
+    const double c2 = fabs(fmin(fmax(k_err4 * e2, -1.0), 1.0));
+    double reward = -((c0 + c1) + c2) / 3.0;
+    const bool done = (t >= 20.0) || (fabs(xo[7]) > max_theta) || (fabs(xo[6]) > max_phi) || (xo[9] < 50.0);
+    if (done) reward += (-1.0 / 0.01) * (20.0 - t) * 2.0;      // check_bounds penalty (:391-399)
+    e.ret += reward;
+    if (ar.trace) {
+        double* tr = ar.trace + (traj * ar.horizon + e.k) * SERL_TRACE_COLS;
+#pragma unroll
+        for (int i = 0; i < 12; ++i) tr[i] = xo[i];
+        tr[12] = U[0]; tr[13] = U[1]; tr[14] = U[2];
+        tr[15] = reward;
+        tr[16] = act_d[0]; tr[17] = act_d[1]; tr[18] = act_d[2];
+        tr[19] = e0; tr[20] = e1; tr[21] = e2;
+    }
+    obs[0] = (float)e0; obs[1] = (float)e1; obs[2] = (float)e2;
+    obs[3] = (float)xo[0]; obs[4] = (float)xo[1]; obs[5] = (float)xo[2]; obs[6] = (float)xo[4];
+    e.t = t + 0.01;
+    e.k += 1;
+    e.done = done || (e.k >= ar.horizon);
+}
+
+// ---- simple actor: every thread evaluates the whole MLP for its own observation -------------------------
+__device__ void actor_forward_simple(const float* __restrict__ w, const serl_actor_shape sh, float* bufA, float* bufB,
+                                     int tid, int nthr, const float* obs, float* action)
 {
     const int S = sh.state_dim, A = sh.action_dim, H = sh.hidden, L = sh.num_layers;
     const float* p = w;
-    // input layer
     for (int j = 0; j < H; ++j) {
         float acc = 0.f;
         for (int i = 0; i < S; ++i) acc = fmaf(p[j * S + i], obs[i], acc);
@@ -157,8 +272,7 @@ __device__ void actor_forward(const float* __restrict__ w, const serl_actor_shap
             const float d = out[j * nthr + tid] - mean;
             ss = fmaf(d, d, ss);
         }
-        const float stdv = sqrtf(ss / (float)(H - 1));
-        const float den = stdv + 1e-6f;
+        const float den = sqrtf(ss / (float)(H - 1)) + 1e-6f;
         for (int j = 0; j < H; ++j) {
             const float d = out[j * nthr + tid] - mean;
             out[j * nthr + tid] = act_fn(sh.activation, gamma[j] * d / den + beta[j]);
@@ -175,113 +289,218 @@ __device__ void actor_forward(const float* __restrict__ w, const serl_actor_shap
 }
 
 __global__ void __launch_bounds__(ROLLOUT_THREADS)
-rollout_kernel_v1(const float* __restrict__ weights, int P, serl_actor_shape sh,
-                  const double* __restrict__ ref_levels, const double* __restrict__ ref_starts,
-                  const int* __restrict__ env_mode, int n_envs, int horizon,
-                  double* __restrict__ returns, int* __restrict__ steps,
-                  double* __restrict__ trace_x, double* __restrict__ trace_u, double* __restrict__ trace_r)
+rollout_kernel_simple(RolloutArgs ar)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* w = reinterpret_cast<float*>(smem_raw);
-    const int P4 = (P + 3) & ~3;
+    const int P4 = (ar.P + 3) & ~3;
     float* bufA = w + P4;
-    float* bufB = bufA + sh.hidden * ROLLOUT_THREADS;
-
-    const int actor = blockIdx.y;
-    const int tid = threadIdx.x;
+    float* bufB = bufA + ar.sh.hidden * ROLLOUT_THREADS;
+    const int actor = blockIdx.y, tid = threadIdx.x;
     const int env = blockIdx.x * ROLLOUT_THREADS + tid;
-    const float* gw = weights + (size_t)actor * P;
-    for (int i = tid; i < P; i += ROLLOUT_THREADS) w[i] = gw[i];
+    const float* gw = ar.weights + (size_t)actor * ar.P;
+    for (int i = tid; i < ar.P; i += ROLLOUT_THREADS) w[i] = gw[i];
     __syncthreads();
-    if (env >= n_envs) return;
-
-    const int mode = env_mode[env];
-    const int variant = mode & 0xff;
-    const int fault = (mode >> 8) & 0xff;
-    double lv[2][SERL_REF_BLOCKS], st[2][SERL_REF_BLOCKS];
-#pragma unroll
-    for (int c = 0; c < 2; ++c)
-#pragma unroll
-        for (int j = 0; j < SERL_REF_BLOCKS; ++j) {
-            lv[c][j] = ref_levels[((size_t)env * 2 + c) * SERL_REF_BLOCKS + j];
-            st[c][j] = ref_starts[((size_t)env * 2 + c) * SERL_REF_BLOCKS + j];
-        }
-
-    const double DEG2RAD = 0.017453292519943295;   // numpy deg2rad multiplier (pi/180)
-    const double RAD2DEG = 57.29577951308232;      // numpy rad2deg multiplier (180/pi)
-    const double bound = 10.0 * DEG2RAD;           // envs/phlabenv.py:208
-    const double max_theta = 60.0 * DEG2RAD, max_phi = 75.0 * DEG2RAD;
-    const double k_err = 6.0 / 3.141592653589793;   // envs/phlabenv.py:226-231
-    const double k_err4 = k_err * 4.0;
-
-    double X[NX];
-    const double* ic = plant_ic(variant);
-#pragma unroll
-    for (int i = 0; i < NX; ++i) X[i] = ic[i];
-
-    // reset(): one zero-command step returns the initial state (phlabenv.py:409-413)
-    double xo[12];
-    double U[3] = {0.0, 0.0, 0.0};
-    double cmd[3];
-    auto apply_fault = [&](const double* u, double* c) {
-        c[0] = u[0]; c[1] = u[1]; c[2] = u[2];
-        if (fault == SERL_FAULT_BE) c[0] = u[0] * 0.3;
-        else if (fault == SERL_FAULT_JR) c[2] = 15 * 3.14159 / 180;
-        else if (fault == SERL_FAULT_SA) { const double b = 1.0 * DEG2RAD; c[1] = fmin(fmax(u[1], -b), b); }
-        else if (fault == SERL_FAULT_SE) { const double b = 2.5 * DEG2RAD; c[0] = fmin(fmax(u[0], -b), b); }
-    };
-#pragma unroll
-    for (int i = 0; i < 12; ++i) xo[i] = X[i];
-    apply_fault(U, cmd);
-    plant_step(variant, X, cmd);
-    const double theta_trim = xo[7] * RAD2DEG;
-
-    float obs[7] = {0.f, 0.f, 0.f, (float)xo[0], (float)xo[1], (float)xo[2], (float)xo[4]};
-    double t = 0.0, ret = 0.0;
-    int k = 0;
-    const size_t traj = (size_t)actor * n_envs + env;
-    for (; k < horizon; ++k) {
-        float a[3];
-        actor_forward(w, sh, bufA, bufB, tid, ROLLOUT_THREADS, obs, a);
-        // scale_action: low + 0.5*(a + 1.0)*(high - low), (a + 1.0) and the halving in float32 (phlabenv.py:72-73)
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            const float t1 = a[i] + 1.0f;
-            const float t2 = 0.5f * t1;
-            U[i] = -bound + (double)t2 * (bound - (-bound));
-        }
-        apply_fault(U, cmd);
-#pragma unroll
-        for (int i = 0; i < 12; ++i) xo[i] = X[i];
-        plant_step(variant, X, cmd);
-
-        const double r_th = ref_deg(lv[0], st[0], t, theta_trim) * DEG2RAD;
-        const double r_ph = ref_deg(lv[1], st[1], t, 0.0) * DEG2RAD;
-        const double e0 = r_th - xo[7], e1 = r_ph - xo[6], e2 = 0.0 - xo[5];
-        const double c0 = fabs(fmin(fmax(k_err * e0, -1.0), 1.0));
-        const double c1 = fabs(fmin(fmax(k_err * e1, -1.0), 1.0));
-        const double c2 = fabs(fmin(fmax(k_err4 * e2, -1.0), 1.0));
-        double reward = -((c0 + c1) + c2) / 3.0;
-        const bool done = (t >= 20.0) || (fabs(xo[7]) > max_theta) || (fabs(xo[6]) > max_phi) || (xo[9] < 50.0);
-        if (done) reward += (-1.0 / 0.01) * (20.0 - t) * 2.0;
-        ret += reward;
-        if (trace_x) {
-            double* tx = trace_x + (traj * horizon + k) * 12;
-#pragma unroll
-            for (int i = 0; i < 12; ++i) tx[i] = xo[i];
-        }
-        if (trace_u) {
-            double* tu = trace_u + (traj * horizon + k) * 3;
-            tu[0] = U[0]; tu[1] = U[1]; tu[2] = U[2];
-        }
-        if (trace_r) trace_r[traj * horizon + k] = reward;
-        obs[0] = (float)e0; obs[1] = (float)e1; obs[2] = (float)e2;
-        obs[3] = (float)xo[0]; obs[4] = (float)xo[1]; obs[5] = (float)xo[2]; obs[6] = (float)xo[4];
-        t += 0.01;
-        if (done) { ++k; break; }
+    if (env >= ar.n_envs) return;
+    Env e;
+    float obs[7], a[3];
+    env_reset(e, ar, env, obs);
+    const size_t traj = (size_t)actor * ar.n_envs + env;
+    while (!e.done) {
+        actor_forward_simple(w, ar.sh, bufA, bufB, tid, ROLLOUT_THREADS, obs, a);
+        env_step(e, ar, traj, a, obs);
     }
-    returns[traj] = ret;
-    steps[traj] = k;
+    ar.returns[traj] = e.ret;
+    ar.steps[traj] = e.k;
+}
+
+// ---- cooperative GEMM actor -----------------------------------------------------------------------------
+// smem: transposed weights  Wt0[S][H] b0[H] | L x { Wt[H][H] b[H] gamma[H] beta[H] } | Wo[A][H] bo[A]
+//       act[H][128] (rows 0..S-1 double as the observation tile), partial[2][4][128]
+// thread (warp og, lane): outputs og*TM .. og*TM+TM-1 of the envs 4*lane .. 4*lane+3.
+template <int H>
+struct GemmCfg {
+    static constexpr int TM = H / 4;
+    static_assert(H % 8 == 0, "hidden must be a multiple of 8");
+};
+
+template <int H>
+__device__ __forceinline__ void gemm_tile(const float* __restrict__ Wt, const float* __restrict__ act, int K, int og, int lane,
+                                          float (&acc)[H / 4][4])
+{
+    constexpr int TM = H / 4;
+#pragma unroll
+    for (int m = 0; m < TM; ++m)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[m][c] = 0.f;
+#pragma unroll 2
+    for (int k = 0; k < K; ++k) {
+        const float4 a4 = *reinterpret_cast<const float4*>(act + k * ROLLOUT_THREADS + 4 * lane);
+        const float2* wp = reinterpret_cast<const float2*>(Wt + k * H + og * TM);
+#pragma unroll
+        for (int m2 = 0; m2 < TM / 2; ++m2) {
+            const float2 w2 = wp[m2];
+            acc[2 * m2][0] = fmaf(w2.x, a4.x, acc[2 * m2][0]);
+            acc[2 * m2][1] = fmaf(w2.x, a4.y, acc[2 * m2][1]);
+            acc[2 * m2][2] = fmaf(w2.x, a4.z, acc[2 * m2][2]);
+            acc[2 * m2][3] = fmaf(w2.x, a4.w, acc[2 * m2][3]);
+            acc[2 * m2 + 1][0] = fmaf(w2.y, a4.x, acc[2 * m2 + 1][0]);
+            acc[2 * m2 + 1][1] = fmaf(w2.y, a4.y, acc[2 * m2 + 1][1]);
+            acc[2 * m2 + 1][2] = fmaf(w2.y, a4.z, acc[2 * m2 + 1][2]);
+            acc[2 * m2 + 1][3] = fmaf(w2.y, a4.w, acc[2 * m2 + 1][3]);
+        }
+    }
+}
+
+template <int H>
+__global__ void __launch_bounds__(ROLLOUT_THREADS, (H <= 72 ? 2 : 1))
+rollout_kernel_gemm(RolloutArgs ar)
+{
+    constexpr int TM = H / 4;
+    constexpr int S = 7, A = 3;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* w = reinterpret_cast<float*>(smem_raw);
+    const int L = ar.sh.num_layers;
+    const int actfn = ar.sh.activation;
+    // smem weight layout (floats)
+    float* Wt0 = w;                       // [S][H]
+    float* b0 = Wt0 + S * H;              // [H]
+    float* hid = b0 + H;                  // L x (H*H + 3H)
+    float* Wo = hid + (size_t)L * (H * H + 3 * H);   // [A][H]
+    float* bo = Wo + A * H;               // [A]
+    const int P4 = (ar.P + 3) & ~3;
+    float* act = w + P4;                  // [H][128]
+    float* part = act + H * ROLLOUT_THREADS;   // [2][4][128]
+
+    const int actor = blockIdx.y, tid = threadIdx.x;
+    const int og = tid >> 5, lane = tid & 31;
+    const int env = blockIdx.x * ROLLOUT_THREADS + tid;
+    // stage the genome: parameters() order in HBM (row-major [out][in]) -> transposed [in][out] in smem
+    {
+        const float* gw = ar.weights + (size_t)actor * ar.P;
+        for (int i = tid; i < ar.P; i += ROLLOUT_THREADS) {
+            const float v = gw[i];
+            int r = i;
+            if (r < S * H) { const int j = r / S, k = r % S; Wt0[k * H + j] = v; continue; }
+            r -= S * H;
+            if (r < H) { b0[r] = v; continue; }
+            r -= H;
+            const int per = H * H + 3 * H;
+            if (r < L * per) {
+                const int l = r / per, q = r % per;
+                float* base = hid + (size_t)l * per;
+                if (q < H * H) { const int j = q / H, k = q % H; base[k * H + j] = v; }
+                else base[q] = v;
+                continue;
+            }
+            r -= L * per;
+            Wo[r] = v;      // Wo [A][H] then bo[A], contiguous
+        }
+    }
+    Env e;
+    float obs[7], a[3];
+    const bool valid = env < ar.n_envs;
+    if (valid) env_reset(e, ar, env, obs);
+    else { e.done = true; e.k = 0; e.ret = 0.0;
+#pragma unroll
+        for (int i = 0; i < 7; ++i) obs[i] = 0.f; }
+    const size_t traj = (size_t)actor * ar.n_envs + (valid ? env : 0);
+    __syncthreads();
+
+    float acc[TM][4];
+    while (true) {
+        // observation tile -> act rows 0..6
+#pragma unroll
+        for (int i = 0; i < S; ++i) act[i * ROLLOUT_THREADS + tid] = obs[i];
+        __syncthreads();
+        // input layer
+        gemm_tile<H>(Wt0, act, S, og, lane, acc);
+        __syncthreads();                                  // every warp has read the observation rows
+#pragma unroll
+        for (int m = 0; m < TM; ++m) {
+            const float b = b0[og * TM + m];
+            float4 o;
+            o.x = act_fn(actfn, acc[m][0] + b); o.y = act_fn(actfn, acc[m][1] + b);
+            o.z = act_fn(actfn, acc[m][2] + b); o.w = act_fn(actfn, acc[m][3] + b);
+            *reinterpret_cast<float4*>(act + (og * TM + m) * ROLLOUT_THREADS + 4 * lane) = o;
+        }
+        __syncthreads();
+        // hidden layers: Linear -> LayerNorm (unbiased std, eps on std) -> activation
+        for (int l = 0; l < L; ++l) {
+            const float* Wt = hid + (size_t)l * (H * H + 3 * H);
+            const float* bb = Wt + H * H;
+            const float* gamma = bb + H;
+            const float* beta = gamma + H;
+            gemm_tile<H>(Wt, act, H, og, lane, acc);
+            float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int m = 0; m < TM; ++m) {
+                const float b = bb[og * TM + m];
+                acc[m][0] += b; acc[m][1] += b; acc[m][2] += b; acc[m][3] += b;
+                s.x += acc[m][0]; s.y += acc[m][1]; s.z += acc[m][2]; s.w += acc[m][3];
+            }
+            *reinterpret_cast<float4*>(part + og * ROLLOUT_THREADS + 4 * lane) = s;
+            __syncthreads();                              // partial sums visible; all reads of act are done
+            float mean[4];
+            {
+                const float4 p0 = *reinterpret_cast<const float4*>(part + 4 * lane);
+                const float4 p1 = *reinterpret_cast<const float4*>(part + ROLLOUT_THREADS + 4 * lane);
+                const float4 p2 = *reinterpret_cast<const float4*>(part + 2 * ROLLOUT_THREADS + 4 * lane);
+                const float4 p3 = *reinterpret_cast<const float4*>(part + 3 * ROLLOUT_THREADS + 4 * lane);
+                mean[0] = (((p0.x + p1.x) + p2.x) + p3.x) / (float)H;
+                mean[1] = (((p0.y + p1.y) + p2.y) + p3.y) / (float)H;
+                mean[2] = (((p0.z + p1.z) + p2.z) + p3.z) / (float)H;
+                mean[3] = (((p0.w + p1.w) + p2.w) + p3.w) / (float)H;
+            }
+            float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int m = 0; m < TM; ++m) {
+                acc[m][0] -= mean[0]; acc[m][1] -= mean[1]; acc[m][2] -= mean[2]; acc[m][3] -= mean[3];
+                q.x = fmaf(acc[m][0], acc[m][0], q.x); q.y = fmaf(acc[m][1], acc[m][1], q.y);
+                q.z = fmaf(acc[m][2], acc[m][2], q.z); q.w = fmaf(acc[m][3], acc[m][3], q.w);
+            }
+            float* part2 = part + 4 * ROLLOUT_THREADS;
+            *reinterpret_cast<float4*>(part2 + og * ROLLOUT_THREADS + 4 * lane) = q;
+            __syncthreads();
+            float den[4];
+            {
+                const float4 p0 = *reinterpret_cast<const float4*>(part2 + 4 * lane);
+                const float4 p1 = *reinterpret_cast<const float4*>(part2 + ROLLOUT_THREADS + 4 * lane);
+                const float4 p2 = *reinterpret_cast<const float4*>(part2 + 2 * ROLLOUT_THREADS + 4 * lane);
+                const float4 p3 = *reinterpret_cast<const float4*>(part2 + 3 * ROLLOUT_THREADS + 4 * lane);
+                den[0] = sqrtf((((p0.x + p1.x) + p2.x) + p3.x) / (float)(H - 1)) + 1e-6f;
+                den[1] = sqrtf((((p0.y + p1.y) + p2.y) + p3.y) / (float)(H - 1)) + 1e-6f;
+                den[2] = sqrtf((((p0.z + p1.z) + p2.z) + p3.z) / (float)(H - 1)) + 1e-6f;
+                den[3] = sqrtf((((p0.w + p1.w) + p2.w) + p3.w) / (float)(H - 1)) + 1e-6f;
+            }
+#pragma unroll
+            for (int m = 0; m < TM; ++m) {
+                const float g = gamma[og * TM + m], be = beta[og * TM + m];
+                float4 o;
+                o.x = act_fn(actfn, g * acc[m][0] / den[0] + be); o.y = act_fn(actfn, g * acc[m][1] / den[1] + be);
+                o.z = act_fn(actfn, g * acc[m][2] / den[2] + be); o.w = act_fn(actfn, g * acc[m][3] / den[3] + be);
+                *reinterpret_cast<float4*>(act + (og * TM + m) * ROLLOUT_THREADS + 4 * lane) = o;
+            }
+            __syncthreads();
+        }
+        // output layer: each thread finishes its own env
+#pragma unroll
+        for (int j = 0; j < A; ++j) {
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll 4
+            for (int k = 0; k < H; k += 2) {
+                s0 = fmaf(Wo[j * H + k], act[k * ROLLOUT_THREADS + tid], s0);
+                s1 = fmaf(Wo[j * H + k + 1], act[(k + 1) * ROLLOUT_THREADS + tid], s1);
+            }
+            a[j] = tanhf((s0 + s1) + bo[j]);
+        }
+        if (!e.done) env_step(e, ar, traj, a, obs);
+        if (!__syncthreads_or(e.done ? 0 : 1)) break;      // also orders the act reads above before the next obs write
+    }
+    if (valid) {
+        ar.returns[traj] = e.ret;
+        ar.steps[traj] = e.k;
+    }
 }
 
 // fitness[a] = mean over envs of returns[a, :]  (base/core/agent.py:245, np.mean over the evaluation axis)
@@ -301,31 +520,59 @@ extern "C" int64_t serl_actor_num_params(const serl_actor_shape* s)
     return S * H + H + L * (H * H + 3 * H) + H * A + A;
 }
 
+static int g_force_simple = -1;
+
+template <int H>
+static cudaError_t launch_gemm(const RolloutArgs& ar, dim3 grid, size_t smem, cudaStream_t s)
+{
+    cudaError_t e = cudaFuncSetAttribute(rollout_kernel_gemm<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    rollout_kernel_gemm<H><<<grid, ROLLOUT_THREADS, smem, s>>>(ar);
+    return cudaGetLastError();
+}
+
 extern "C" int serl_rollout(const float* d_weights, int32_t pop, const serl_actor_shape* shape,
                             const double* d_ref_levels, const double* d_ref_starts, const int32_t* d_env_mode,
-                            int32_t n_envs, int32_t horizon,
-                            double* d_returns, int32_t* d_steps, double* d_fitness,
-                            double* d_trace_x, double* d_trace_u, double* d_trace_r, void* stream)
+                            int32_t n_envs, int32_t horizon, const float* d_action_noise,
+                            double* d_returns, int32_t* d_steps, double* d_fitness, double* d_trace, void* stream)
 {
     if (!d_weights || !shape || !d_ref_levels || !d_ref_starts || !d_env_mode || !d_returns || !d_steps)
         return serl_fail(SERL_ERR_ARG, "serl_rollout: null pointer argument");
     if (pop <= 0 || n_envs <= 0 || horizon <= 0) return serl_fail(SERL_ERR_ARG, "serl_rollout: pop, n_envs, horizon must be > 0");
+    if (pop > 65535) return serl_fail(SERL_ERR_ARG, "serl_rollout: pop must be <= 65535 per call");
     if (shape->state_dim != 7 || shape->action_dim != 3)
         return serl_fail(SERL_ERR_ARG, "serl_rollout: PH-LAB attitude task needs state_dim=7, action_dim=3");
     if (shape->hidden < 2 || shape->hidden > 256 || shape->num_layers < 0 || shape->activation < 0 || shape->activation > 2)
         return serl_fail(SERL_ERR_ARG, "serl_rollout: unsupported actor shape");
+    if (g_force_simple < 0) {
+        const char* v = getenv("SERL_ROLLOUT_IMPL");
+        g_force_simple = (v && strcmp(v, "simple") == 0) ? 1 : 0;
+    }
     cudaStream_t s = (cudaStream_t)stream;
-    const int P = (int)serl_actor_num_params(shape);
-    const int P4 = (P + 3) & ~3;
-    const size_t smem = (size_t)P4 * 4 + 2ull * shape->hidden * ROLLOUT_THREADS * 4;
-    if (smem > 227 * 1024) return serl_fail(SERL_ERR_UNSUPPORTED, "serl_rollout: genome + activations exceed 227 KB of shared memory");
-    cudaError_t e = cudaFuncSetAttribute(rollout_kernel_v1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return serl_fail_cuda(e, "cudaFuncSetAttribute(rollout)");
+    RolloutArgs ar;
+    ar.weights = d_weights; ar.P = (int)serl_actor_num_params(shape); ar.sh = *shape;
+    ar.ref_levels = d_ref_levels; ar.ref_starts = d_ref_starts; ar.env_mode = d_env_mode; ar.n_envs = n_envs; ar.horizon = horizon;
+    ar.action_noise = d_action_noise; ar.returns = d_returns; ar.steps = d_steps; ar.trace = d_trace;
+    const int P4 = (ar.P + 3) & ~3;
+    const int H = shape->hidden;
     dim3 grid((n_envs + ROLLOUT_THREADS - 1) / ROLLOUT_THREADS, pop);
-    rollout_kernel_v1<<<grid, ROLLOUT_THREADS, smem, s>>>(d_weights, P, *shape, d_ref_levels, d_ref_starts, d_env_mode,
-                                                          n_envs, horizon, d_returns, d_steps, d_trace_x, d_trace_u, d_trace_r);
+    cudaError_t e;
+    const size_t smem_gemm = (size_t)P4 * 4 + (size_t)H * ROLLOUT_THREADS * 4 + 8 * ROLLOUT_THREADS * 4;
+    const bool gemm_ok = !g_force_simple && (H == 32 || H == 64 || H == 72 || H == 96) && smem_gemm <= 227 * 1024;
+    if (gemm_ok) {
+        if (H == 32) e = launch_gemm<32>(ar, grid, smem_gemm, s);
+        else if (H == 64) e = launch_gemm<64>(ar, grid, smem_gemm, s);
+        else if (H == 72) e = launch_gemm<72>(ar, grid, smem_gemm, s);
+        else e = launch_gemm<96>(ar, grid, smem_gemm, s);
+    } else {
+        const size_t smem = (size_t)P4 * 4 + 2ull * H * ROLLOUT_THREADS * 4;
+        if (smem > 227 * 1024) return serl_fail(SERL_ERR_UNSUPPORTED, "serl_rollout: genome + activations exceed 227 KB of shared memory");
+        e = cudaFuncSetAttribute(rollout_kernel_simple, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return serl_fail_cuda(e, "cudaFuncSetAttribute(rollout)");
+        rollout_kernel_simple<<<grid, ROLLOUT_THREADS, smem, s>>>(ar);
+        e = cudaGetLastError();
+    }
     serl_count_launch();
-    e = cudaGetLastError();
     if (e != cudaSuccess) return serl_fail_cuda(e, "rollout_kernel launch");
     if (d_fitness) {
         fitness_mean_kernel<<<(pop + 127) / 128, 128, 0, s>>>(d_returns, pop, n_envs, d_fitness);

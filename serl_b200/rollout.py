@@ -39,10 +39,20 @@ def _ptr(t):
 
 
 class RolloutResult:
-    __slots__ = ('returns', 'steps', 'fitness', 'trace_x', 'trace_u', 'trace_r')
+    __slots__ = ('returns', 'steps', 'fitness', 'trace')
+
+    # views into the trace record (include/serl_b200.h: SERL_TRACE_COLS)
+    trace_x = property(lambda s: s.trace[..., 0:12])
+    trace_u = property(lambda s: s.trace[..., 12:15])
+    trace_r = property(lambda s: s.trace[..., 15])
+    trace_a = property(lambda s: s.trace[..., 16:19])
+    trace_err = property(lambda s: s.trace[..., 19:22])
 
 
-def population_rollout(weights, shape, ref_levels, ref_starts, env_mode, horizon=HORIZON, trace=False, out=None):
+TRACE_COLS = 22
+
+
+def population_rollout(weights, shape, ref_levels, ref_starts, env_mode, horizon=HORIZON, trace=False, out=None, action_noise=None):
     """weights [pop,P] fp32 cuda; ref_levels/ref_starts [n_envs,2,6] f64 cuda; env_mode [n_envs] int32 cuda."""
     if not weights.is_cuda:
         raise _native.NativeError('population_rollout needs CUDA tensors (no CPU fallback)')
@@ -54,20 +64,20 @@ def population_rollout(weights, shape, ref_levels, ref_starts, env_mode, horizon
     assert ref_levels.shape == (n_envs, 2, 6) and ref_levels.dtype == torch.float64 and ref_levels.is_contiguous()
     assert ref_starts.shape == (n_envs, 2, 6) and ref_starts.dtype == torch.float64 and ref_starts.is_contiguous()
     assert env_mode.dtype == torch.int32
+    if action_noise is not None:
+        assert action_noise.shape == (pop, n_envs, horizon, 3) and action_noise.dtype == torch.float32 and action_noise.is_contiguous()
     dev = weights.device
     r = out if out is not None else RolloutResult()
     if out is None:
         r.returns = torch.empty((pop, n_envs), dtype=torch.float64, device=dev)
         r.steps = torch.empty((pop, n_envs), dtype=torch.int32, device=dev)
         r.fitness = torch.empty((pop,), dtype=torch.float64, device=dev)
-        r.trace_x = r.trace_u = r.trace_r = None
+        r.trace = None
         if trace:
-            r.trace_x = torch.full((pop, n_envs, horizon, 12), float('nan'), dtype=torch.float64, device=dev)
-            r.trace_u = torch.full((pop, n_envs, horizon, 3), float('nan'), dtype=torch.float64, device=dev)
-            r.trace_r = torch.full((pop, n_envs, horizon), float('nan'), dtype=torch.float64, device=dev)
+            r.trace = torch.full((pop, n_envs, horizon, TRACE_COLS), float('nan'), dtype=torch.float64, device=dev)
     stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
     rc = L.serl_rollout(_ptr(weights), pop, ctypes.byref(shape), _ptr(ref_levels), _ptr(ref_starts), _ptr(env_mode),
-                        n_envs, horizon, _ptr(r.returns), _ptr(r.steps), _ptr(r.fitness),
-                        _ptr(r.trace_x), _ptr(r.trace_u), _ptr(r.trace_r), stream)
+                        n_envs, horizon, _ptr(action_noise), _ptr(r.returns), _ptr(r.steps), _ptr(r.fitness),
+                        _ptr(r.trace), stream)
     _native.check(rc, 'serl_rollout')
     return r

@@ -100,6 +100,53 @@ def test_trace_matches_oracle_trajectory():
     assert np.abs(r.trace_r[0, 0, :n].cpu().numpy() - o['rewards']).max() < 1e-4
 
 
+def test_simple_and_gemm_actor_kernels_agree(monkeypatch):
+    """the per-thread MLP kernel and the cooperative-GEMM kernel are two implementations of the same actor."""
+    import subprocess, sys, json
+    code = ("import sys, json, numpy as np, torch; sys.path.insert(0, %r); sys.path.insert(0, %r);"
+            "import test_rollout_gpu as T; from oracle import refsig;"
+            "w = T.ACT['serl10_pop_h72_tanh'][:3]; lv, st = refsig.make_ref_params(5, seed_base=77);"
+            "r = T.gpu_rollout(w, 72, 'tanh', lv, st, ['nominal', 'be', 'ice', 'sa', 'cg']);"
+            "print(json.dumps([r.returns.cpu().tolist(), r.steps.cpu().tolist()]))") % (
+        os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for impl in ('gemm', 'simple'):
+        env = dict(os.environ, SERL_ROLLOUT_IMPL=impl)
+        p = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, env=env, timeout=600)
+        assert p.returncode == 0, p.stderr
+        outs.append(json.loads(p.stdout.strip().splitlines()[-1]))
+    assert outs[0][1] == outs[1][1]
+    assert np.allclose(np.array(outs[0][0]), np.array(outs[1][0]), rtol=1e-5, atol=0)
+
+
+def test_action_noise_path():
+    """is_action_noise=True episodes (agent.py:90-96): noise added in float64, action clipped, scaled in float64."""
+    from serl_b200 import rollout
+    w = ACT['serl10_elite_h72_tanh'][None]
+    lv, st = refsig.make_ref_params(1, seed_base=8)
+    rng = np.random.RandomState(3)
+    noise = np.clip(0.2962183114680794 * rng.randn(1, 1, 2001, 3), -0.5, 0.5)
+    dev = torch.device('cuda:0')
+    sh = rollout.actor_shape(72)
+    md = torch.tensor([rollout.mode_code('nominal')], dtype=torch.int32, device=dev)
+    r = rollout.population_rollout(torch.as_tensor(w, device=dev), sh, torch.as_tensor(lv, device=dev), torch.as_tensor(st, device=dev), md,
+                                   trace=True, action_noise=torch.as_tensor(noise.astype(np.float32), device=dev))
+    torch.cuda.synchronize()
+    # oracle: same loop with the same (float32-rounded) noise
+    env = phlab.CitationEnv('nominal', 'auto')
+    act = A.unflatten(w[0], hidden=72)
+    obs = env.reset(lv[0], st[0])
+    tot, k, done = 0.0, 0, False
+    nz = noise.astype(np.float32).astype(np.float64)
+    while not done:
+        a = np.clip(act.select_action(obs) + nz[0, 0, k], -1.0, 1.0)
+        obs, rew, done, _ = env.step(a.flatten())
+        tot += rew
+        k += 1
+    assert int(r.steps[0, 0]) == k
+    assert abs(float(r.returns[0, 0]) - tot) <= REL_TOL * abs(tot)
+
+
 def test_ragged_env_count_and_many_actors():
     """n_envs not a multiple of the CTA size, more actors than SMs: every trajectory must be written."""
     w = np.tile(ACT['serl50_pop8_h32_tanh'], (25, 1))          # 200 actors
