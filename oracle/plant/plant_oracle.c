@@ -26,6 +26,7 @@ typedef double real;
 #define PLANT_EXP exp
 #define PLANT_LOG10 log10
 #define PLANT_POW pow
+#define PLANT_XARGS
 #include "plant_support.h"
 #include "gen/plant_tables.h"
 #include "gen/plant_rhs_h2000_v90.h"

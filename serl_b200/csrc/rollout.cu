@@ -11,8 +11,10 @@
 // (genome, reference-signal parameters) and end (return, step count) unless a trace is requested.
 //
 // Two actor implementations:
-//   rollout_kernel_gemm<H>  block-cooperative register-tiled GEMM: warp = 1/4 of the output neurons, lane = 4 envs;
-//                           weights transposed in smem, one activation buffer -> 2 CTAs/SM at h=72.  (h in {32,64,72,96})
+//   rollout_kernel_warp<H>  warp-autonomous: a warp owns 32 envs of one actor and never synchronises with other
+//                           warps.  The MLP is a register-tiled GEMM inside the warp (lane = 1/4 of the output neurons
+//                           x 4 envs, activations exchanged with warp shuffles, weights broadcast from shared memory);
+//                           plant tables live in shared memory next to the genomes.      (h in {32,64,72,96})
 //   rollout_kernel_simple   every thread runs the whole MLP for its env (any h that fits); reference / fallback shape.
 #include <cuda_runtime.h>
 #include <math.h>
@@ -24,8 +26,10 @@
 #include "common.cuh"
 
 typedef double real;
-#define PLANT_TABLE(name, n) static __device__ const double name[n]
-#define PLANT_TAB(name) name
+// lookup tables: one blob (gen/plant_tables_blob.h) that the kernels stage into shared memory; the generated
+// right-hand sides address it through the `plant_tab` pointer they are handed.
+#define PLANT_TAB(name) (plant_tab + PT_OFF_##name)
+#define PLANT_XARGS , const double* __restrict__ plant_tab
 #define PLANT_IC(v) static __device__ const double plant_ic_##v[19]
 #define PLANT_SQRT sqrt
 #define PLANT_FABS fabs
@@ -39,7 +43,7 @@ typedef double real;
 #include "plant_support.h"
 #undef PLANT_FN
 #define PLANT_FN static __device__ __noinline__
-#include "gen/plant_tables.h"
+#include "gen/plant_tables_blob.h"
 #include "gen/plant_rhs_h2000_v90.h"
 #include "gen/plant_rhs_ice.h"
 #include "gen/plant_rhs_cg.h"
@@ -52,15 +56,15 @@ typedef double real;
 
 // live continuous states of the plant: p q r V alpha beta phi theta | h | washout | N1 N1 N2 N2
 // (psi, x_e, y_e never feed back and are integrated only for traces; Parameter_CSTATE(_g) are folded constants).
-__device__ __forceinline__ void plant_rhs(int variant, const double* X, const double* U, double* xdot)
+__device__ __forceinline__ void plant_rhs(int variant, const double* X, const double* U, double* xdot, const double* tab)
 {
     switch (variant) {
-    case SERL_PLANT_ICE: plant_rhs_ice(X, U, xdot); break;
-    case SERL_PLANT_CG: plant_rhs_cg(X, U, xdot); break;
-    case SERL_PLANT_CG_FOR: plant_rhs_cg_for(X, U, xdot); break;
-    case SERL_PLANT_H2000_V150: plant_rhs_h2000_v150(X, U, xdot); break;
-    case SERL_PLANT_H10000_V90: plant_rhs_h10000_v90(X, U, xdot); break;
-    default: plant_rhs_h2000_v90(X, U, xdot); break;
+    case SERL_PLANT_ICE: plant_rhs_ice(X, U, xdot, tab); break;
+    case SERL_PLANT_CG: plant_rhs_cg(X, U, xdot, tab); break;
+    case SERL_PLANT_CG_FOR: plant_rhs_cg_for(X, U, xdot, tab); break;
+    case SERL_PLANT_H2000_V150: plant_rhs_h2000_v150(X, U, xdot, tab); break;
+    case SERL_PLANT_H10000_V90: plant_rhs_h10000_v90(X, U, xdot, tab); break;
+    default: plant_rhs_h2000_v90(X, U, xdot, tab); break;
     }
 }
 
@@ -77,33 +81,36 @@ __device__ __forceinline__ const double* plant_ic(int variant)
 }
 
 // Simulink fixed-step ode5 exactly as inlined in the reference's step(): stage states are
-// y + (f0*hB0 + f1*hB1 + ...) with hB = h*B[s][j], summed left to right.
-__device__ void plant_step(int variant, double* X, const double* U)
+// y + (f0*hB0 + f1*hB1 + ...) with hB = h*B[s][j], summed left to right (zero coefficients included).
+// Fully unrolled so that every f[j][i] load of a stage is independent and the h*B products fold to constants.
+__device__ void plant_step(int variant, double* X, const double* U, const double* tab)
 {
-    const double h = 0.01;
-    const double B[6][6] = {
+    constexpr double h = 0.01;
+    constexpr double B[6][6] = {
         {1.0 / 5.0, 0, 0, 0, 0, 0},
         {3.0 / 40.0, 9.0 / 40.0, 0, 0, 0, 0},
         {44.0 / 45.0, -56.0 / 15.0, 32.0 / 9.0, 0, 0, 0},
         {19372.0 / 6561.0, -25360.0 / 2187.0, 64448.0 / 6561.0, -212.0 / 729.0, 0, 0},
         {9017.0 / 3168.0, -355.0 / 33.0, 46732.0 / 5247.0, 49.0 / 176.0, -5103.0 / 18656.0, 0},
         {35.0 / 384.0, 0, 500.0 / 1113.0, 125.0 / 192.0, -2187.0 / 6784.0, 11.0 / 84.0}};
+    constexpr int LIVE[14] = {0, 1, 2, 3, 4, 5, 6, 7, 9, 12, 15, 16, 17, 18};
     double f[6][NX], x[NX];
 #pragma unroll
     for (int i = 0; i < NX; ++i) { x[i] = X[i]; }
-#pragma unroll 1
-    for (int s = 0; s < 6; ++s) {
 #pragma unroll
-        for (int i = 0; i < NX; ++i) f[s][i] = 0.0;
-        plant_rhs(variant, x, U, f[s]);
-        for (int i = 0; i < NX; ++i) {
+    for (int s = 0; s < 6; ++s) {
+        plant_rhs(variant, x, U, f[s], tab);
+#pragma unroll
+        for (int li = 0; li < 14; ++li) {
+            const int i = LIVE[li];
             double acc = f[0][i] * (h * B[s][0]);
+#pragma unroll
             for (int j = 1; j <= s; ++j) acc += f[j][i] * (h * B[s][j]);
             x[i] = X[i] + acc;
         }
     }
 #pragma unroll
-    for (int i = 0; i < NX; ++i) X[i] = x[i];
+    for (int li = 0; li < 14; ++li) X[LIVE[li]] = x[LIVE[li]];
 }
 
 __device__ __forceinline__ float act_fn(int act, float x)
@@ -114,7 +121,7 @@ __device__ __forceinline__ float act_fn(int act, float x)
 }
 
 // reference-signal value in degrees (serl_b200/refsig.py; recovered shape of signals.RandomizedCosineStepSequence)
-__device__ __forceinline__ double ref_deg(const double* lv, const double* st, double t, double offset)
+__device__ __forceinline__ double ref_deg(const double* __restrict__ lv, const double* __restrict__ st, double t, double offset)
 {
     int k = 0;
 #pragma unroll
@@ -132,11 +139,14 @@ struct RolloutArgs {
     const double* ref_levels; const double* ref_starts; const int* env_mode; int n_envs; int horizon;
     const float* action_noise;      // optional [pop, n_envs, horizon, 3]: clipped exploration noise (agent.py:90-93)
     double* returns; int* steps; double* trace;   // trace optional [pop, n_envs, horizon, SERL_TRACE_COLS]
+    int pop;
 };
 
 struct Env {
     double X[NX];
-    double lv[2][SERL_REF_BLOCKS], st[2][SERL_REF_BLOCKS];
+    const double* tab;       // plant tables (shared or global memory)
+    const double* ref_lv;    // this env's reference-signal levels / starts [2][SERL_REF_BLOCKS] (global, read per step)
+    const double* ref_st;
     double t, ret, theta_trim;
     int variant, fault, k;
     bool done;
@@ -160,13 +170,8 @@ __device__ void env_reset(Env& e, const RolloutArgs& a, int env, float* obs)
     const int mode = a.env_mode[env];
     e.variant = mode & 0xff;
     e.fault = (mode >> 8) & 0xff;
-#pragma unroll
-    for (int c = 0; c < 2; ++c)
-#pragma unroll
-        for (int j = 0; j < SERL_REF_BLOCKS; ++j) {
-            e.lv[c][j] = a.ref_levels[((size_t)env * 2 + c) * SERL_REF_BLOCKS + j];
-            e.st[c][j] = a.ref_starts[((size_t)env * 2 + c) * SERL_REF_BLOCKS + j];
-        }
+    e.ref_lv = a.ref_levels + (size_t)env * 2 * SERL_REF_BLOCKS;
+    e.ref_st = a.ref_starts + (size_t)env * 2 * SERL_REF_BLOCKS;
     const double* ic = plant_ic(e.variant);
 #pragma unroll
     for (int i = 0; i < NX; ++i) e.X[i] = ic[i];
@@ -175,7 +180,7 @@ __device__ void env_reset(Env& e, const RolloutArgs& a, int env, float* obs)
     e.theta_trim = e.X[7] * RAD2DEG;
     double U[3] = {0.0, 0.0, 0.0}, cmd[3];
     apply_fault(e.fault, U, cmd);
-    plant_step(e.variant, e.X, cmd);
+    plant_step(e.variant, e.X, cmd, e.tab);
     e.t = 0.0; e.ret = 0.0; e.k = 0; e.done = false;
 }
 
@@ -209,11 +214,11 @@ __device__ void env_step(Env& e, const RolloutArgs& ar, size_t traj, const float
     double xo[12];
 #pragma unroll
     for (int i = 0; i < 12; ++i) xo[i] = e.X[i];
-    plant_step(e.variant, e.X, cmd);
+    plant_step(e.variant, e.X, cmd, e.tab);
 
     const double t = e.t;
-    const double r_th = ref_deg(e.lv[0], e.st[0], t, e.theta_trim) * DEG2RAD;
-    const double r_ph = ref_deg(e.lv[1], e.st[1], t, 0.0) * DEG2RAD;
+    const double r_th = ref_deg(e.ref_lv, e.ref_st, t, e.theta_trim) * DEG2RAD;
+    const double r_ph = ref_deg(e.ref_lv + SERL_REF_BLOCKS, e.ref_st + SERL_REF_BLOCKS, t, 0.0) * DEG2RAD;
     const double e0 = r_th - xo[7], e1 = r_ph - xo[6], e2 = 0.0 - xo[5];
     const double c0 = fabs(fmin(fmax(k_err * e0, -1.0), 1.0));
     const double c1 = fabs(fmin(fmax(k_err * e1, -1.0), 1.0));
@@ -303,6 +308,7 @@ rollout_kernel_simple(RolloutArgs ar)
     __syncthreads();
     if (env >= ar.n_envs) return;
     Env e;
+    e.tab = plant_tables_blob;
     float obs[7], a[3];
     env_reset(e, ar, env, obs);
     const size_t traj = (size_t)actor * ar.n_envs + env;
@@ -314,71 +320,165 @@ rollout_kernel_simple(RolloutArgs ar)
     ar.steps[traj] = e.k;
 }
 
-// ---- cooperative GEMM actor -----------------------------------------------------------------------------
-// smem: transposed weights  Wt0[S][H] b0[H] | L x { Wt[H][H] b[H] gamma[H] beta[H] } | Wo[A][H] bo[A]
-//       act[H][128] (rows 0..S-1 double as the observation tile), partial[2][4][128]
-// thread (warp og, lane): outputs og*TM .. og*TM+TM-1 of the envs 4*lane .. 4*lane+3.
+// ---- warp-autonomous actor + env ---------------------------------------------------------------------------
+// smem: plant tables [PT_TOTAL] f64 | per actor of the CTA: transposed weights
+//       Wt0[S][H] b0[H] | L x { Wt[H][H] b[H] gamma[H] beta[H] } | Wo[A][H] bo[A]
+// lane = (g = lane>>2, og = lane&3): output neurons og*TM .. og*TM+TM-1 of the envs 4g .. 4g+3 of this warp.
+// The activation of neuron k for env 4g+c lives in lane (g, og = k/TM), register in[k%TM][c]; the next layer
+// fetches it with one shuffle per (k, c).  Reductions over neurons are xor-butterflies over the two og bits, so
+// the four lanes of a group hold bit-identical means / deviations.
 template <int H>
-struct GemmCfg {
-    static constexpr int TM = H / 4;
-    static_assert(H % 8 == 0, "hidden must be a multiple of 8");
-};
-
-template <int H>
-__device__ __forceinline__ void gemm_tile(const float* __restrict__ Wt, const float* __restrict__ act, int K, int og, int lane,
-                                          float (&acc)[H / 4][4])
+__device__ __forceinline__ void warp_layer(const float* __restrict__ Wt, const float (&in)[H / 4][4], float (&acc)[H / 4][4],
+                                           int og, int lane)
 {
     constexpr int TM = H / 4;
 #pragma unroll
     for (int m = 0; m < TM; ++m)
 #pragma unroll
         for (int c = 0; c < 4; ++c) acc[m][c] = 0.f;
-#pragma unroll 2
-    for (int k = 0; k < K; ++k) {
-        const float4 a4 = *reinterpret_cast<const float4*>(act + k * ROLLOUT_THREADS + 4 * lane);
-        const float2* wp = reinterpret_cast<const float2*>(Wt + k * H + og * TM);
+    const int gbase = lane & ~3;
+#pragma unroll 1
+    for (int so = 0; so < 4; ++so) {
+        const float* wrow = Wt + (size_t)(so * TM) * H + og * TM;
 #pragma unroll
-        for (int m2 = 0; m2 < TM / 2; ++m2) {
-            const float2 w2 = wp[m2];
-            acc[2 * m2][0] = fmaf(w2.x, a4.x, acc[2 * m2][0]);
-            acc[2 * m2][1] = fmaf(w2.x, a4.y, acc[2 * m2][1]);
-            acc[2 * m2][2] = fmaf(w2.x, a4.z, acc[2 * m2][2]);
-            acc[2 * m2][3] = fmaf(w2.x, a4.w, acc[2 * m2][3]);
-            acc[2 * m2 + 1][0] = fmaf(w2.y, a4.x, acc[2 * m2 + 1][0]);
-            acc[2 * m2 + 1][1] = fmaf(w2.y, a4.y, acc[2 * m2 + 1][1]);
-            acc[2 * m2 + 1][2] = fmaf(w2.y, a4.z, acc[2 * m2 + 1][2]);
-            acc[2 * m2 + 1][3] = fmaf(w2.y, a4.w, acc[2 * m2 + 1][3]);
+        for (int m = 0; m < TM; ++m) {
+            const float a0 = __shfl_sync(0xffffffffu, in[m][0], gbase + so);
+            const float a1 = __shfl_sync(0xffffffffu, in[m][1], gbase + so);
+            const float a2 = __shfl_sync(0xffffffffu, in[m][2], gbase + so);
+            const float a3 = __shfl_sync(0xffffffffu, in[m][3], gbase + so);
+            const float2* wp = reinterpret_cast<const float2*>(wrow + m * H);
+#pragma unroll
+            for (int m2 = 0; m2 < TM / 2; ++m2) {
+                const float2 w2 = wp[m2];
+                acc[2 * m2][0] = fmaf(w2.x, a0, acc[2 * m2][0]);
+                acc[2 * m2][1] = fmaf(w2.x, a1, acc[2 * m2][1]);
+                acc[2 * m2][2] = fmaf(w2.x, a2, acc[2 * m2][2]);
+                acc[2 * m2][3] = fmaf(w2.x, a3, acc[2 * m2][3]);
+                acc[2 * m2 + 1][0] = fmaf(w2.y, a0, acc[2 * m2 + 1][0]);
+                acc[2 * m2 + 1][1] = fmaf(w2.y, a1, acc[2 * m2 + 1][1]);
+                acc[2 * m2 + 1][2] = fmaf(w2.y, a2, acc[2 * m2 + 1][2]);
+                acc[2 * m2 + 1][3] = fmaf(w2.y, a3, acc[2 * m2 + 1][3]);
+            }
         }
     }
 }
 
+__device__ __forceinline__ float group_sum(float v)
+{
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    return v;
+}
+
 template <int H>
-__global__ void __launch_bounds__(ROLLOUT_THREADS, (H <= 72 ? 2 : 1))
-rollout_kernel_gemm(RolloutArgs ar)
+__device__ void actor_forward_warp(const float* __restrict__ w, int L, int actfn, int lane, const float* obs, float* action)
 {
     constexpr int TM = H / 4;
     constexpr int S = 7, A = 3;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* w = reinterpret_cast<float*>(smem_raw);
-    const int L = ar.sh.num_layers;
-    const int actfn = ar.sh.activation;
-    // smem weight layout (floats)
-    float* Wt0 = w;                       // [S][H]
-    float* b0 = Wt0 + S * H;              // [H]
-    float* hid = b0 + H;                  // L x (H*H + 3H)
-    float* Wo = hid + (size_t)L * (H * H + 3 * H);   // [A][H]
-    float* bo = Wo + A * H;               // [A]
-    const int P4 = (ar.P + 3) & ~3;
-    float* act = w + P4;                  // [H][128]
-    float* part = act + H * ROLLOUT_THREADS;   // [2][4][128]
+    const int og = lane & 3, gbase = lane & ~3;
+    const float* Wt0 = w;
+    const float* b0 = Wt0 + S * H;
+    const float* hid = b0 + H;
+    const float* Wo = hid + (size_t)L * (H * H + 3 * H);
+    const float* bo = Wo + A * H;
+    float in[TM][4], acc[TM][4];
+    // input layer: observation of env 4g+c lives in lane gbase+c
+#pragma unroll
+    for (int m = 0; m < TM; ++m)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[m][c] = 0.f;
+#pragma unroll
+    for (int k = 0; k < S; ++k) {
+        const float a0 = __shfl_sync(0xffffffffu, obs[k], gbase + 0);
+        const float a1 = __shfl_sync(0xffffffffu, obs[k], gbase + 1);
+        const float a2 = __shfl_sync(0xffffffffu, obs[k], gbase + 2);
+        const float a3 = __shfl_sync(0xffffffffu, obs[k], gbase + 3);
+#pragma unroll
+        for (int m = 0; m < TM; ++m) {
+            const float wv = Wt0[k * H + og * TM + m];
+            acc[m][0] = fmaf(wv, a0, acc[m][0]); acc[m][1] = fmaf(wv, a1, acc[m][1]);
+            acc[m][2] = fmaf(wv, a2, acc[m][2]); acc[m][3] = fmaf(wv, a3, acc[m][3]);
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < TM; ++m) {
+        const float b = b0[og * TM + m];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) in[m][c] = act_fn(actfn, acc[m][c] + b);
+    }
+    // hidden layers: Linear -> LayerNorm (unbiased std, eps on std; mod_utils.py:47-50) -> activation
+#pragma unroll 1
+    for (int l = 0; l < L; ++l) {
+        const float* Wt = hid + (size_t)l * (H * H + 3 * H);
+        const float* bb = Wt + H * H;
+        const float* gamma = bb + H;
+        const float* beta = gamma + H;
+        warp_layer<H>(Wt, in, acc, og, lane);
+        float s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int m = 0; m < TM; ++m) {
+            const float b = bb[og * TM + m];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { acc[m][c] += b; s[c] += acc[m][c]; }
+        }
+        float mean[4], den[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) mean[c] = group_sum(s[c]) / (float)H;
+        float q[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int m = 0; m < TM; ++m)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { acc[m][c] -= mean[c]; q[c] = fmaf(acc[m][c], acc[m][c], q[c]); }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) den[c] = sqrtf(group_sum(q[c]) / (float)(H - 1)) + 1e-6f;
+#pragma unroll
+        for (int m = 0; m < TM; ++m) {
+            const float g = gamma[og * TM + m], be = beta[og * TM + m];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) in[m][c] = act_fn(actfn, g * acc[m][c] / den[c] + be);
+        }
+    }
+    // output layer: partial dot products over this lane's neurons, reduced over the group; lane og keeps env 4g+og
+#pragma unroll
+    for (int j = 0; j < A; ++j) {
+        float p[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int m = 0; m < TM; ++m) {
+            const float wv = Wo[j * H + og * TM + m];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) p[c] = fmaf(wv, in[m][c], p[c]);
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) p[c] = group_sum(p[c]);
+        const float mine = og == 0 ? p[0] : (og == 1 ? p[1] : (og == 2 ? p[2] : p[3]));
+        action[j] = tanhf(mine + bo[j]);
+    }
+}
 
-    const int actor = blockIdx.y, tid = threadIdx.x;
-    const int og = tid >> 5, lane = tid & 31;
-    const int env = blockIdx.x * ROLLOUT_THREADS + tid;
-    // stage the genome: parameters() order in HBM (row-major [out][in]) -> transposed [in][out] in smem
-    {
-        const float* gw = ar.weights + (size_t)actor * ar.P;
-        for (int i = tid; i < ar.P; i += ROLLOUT_THREADS) {
+template <int H, int APC>
+__global__ void __launch_bounds__(ROLLOUT_THREADS * APC, 1)
+rollout_kernel_warp(RolloutArgs ar)
+{
+    constexpr int S = 7;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* tab = reinterpret_cast<double*>(smem_raw);
+    float* wbase = reinterpret_cast<float*>(tab + PT_TOTAL);
+    const int L = ar.sh.num_layers;
+    const int P4 = (ar.P + 3) & ~3;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int al = warp >> 2;                               // actor slot of this warp inside the CTA
+    const int actor = blockIdx.y * APC + al;
+    const int env = blockIdx.x * ROLLOUT_THREADS + (warp & 3) * 32 + lane;
+    for (int i = tid; i < PT_TOTAL; i += ROLLOUT_THREADS * APC) tab[i] = plant_tables_blob[i];
+    // stage the genomes: parameters() order in HBM (row-major [out][in]) -> transposed [in][out] in smem
+    for (int slot = 0; slot < APC; ++slot) {
+        const int ga = blockIdx.y * APC + slot;
+        if (ga >= ar.pop) break;
+        const float* gw = ar.weights + (size_t)ga * ar.P;
+        float* w = wbase + (size_t)slot * P4;
+        float* Wt0 = w; float* b0 = Wt0 + S * H; float* hid = b0 + H;
+        float* Wo = hid + (size_t)L * (H * H + 3 * H);
+        for (int i = tid; i < ar.P; i += ROLLOUT_THREADS * APC) {
             const float v = gw[i];
             int r = i;
             if (r < S * H) { const int j = r / S, k = r % S; Wt0[k * H + j] = v; continue; }
@@ -397,7 +497,11 @@ rollout_kernel_gemm(RolloutArgs ar)
             Wo[r] = v;      // Wo [A][H] then bo[A], contiguous
         }
     }
+    __syncthreads();
+    if (actor >= ar.pop) return;
+    const float* w = wbase + (size_t)al * P4;
     Env e;
+    e.tab = tab;
     float obs[7], a[3];
     const bool valid = env < ar.n_envs;
     if (valid) env_reset(e, ar, env, obs);
@@ -405,97 +509,9 @@ rollout_kernel_gemm(RolloutArgs ar)
 #pragma unroll
         for (int i = 0; i < 7; ++i) obs[i] = 0.f; }
     const size_t traj = (size_t)actor * ar.n_envs + (valid ? env : 0);
-    __syncthreads();
-
-    float acc[TM][4];
-    while (true) {
-        // observation tile -> act rows 0..6
-#pragma unroll
-        for (int i = 0; i < S; ++i) act[i * ROLLOUT_THREADS + tid] = obs[i];
-        __syncthreads();
-        // input layer
-        gemm_tile<H>(Wt0, act, S, og, lane, acc);
-        __syncthreads();                                  // every warp has read the observation rows
-#pragma unroll
-        for (int m = 0; m < TM; ++m) {
-            const float b = b0[og * TM + m];
-            float4 o;
-            o.x = act_fn(actfn, acc[m][0] + b); o.y = act_fn(actfn, acc[m][1] + b);
-            o.z = act_fn(actfn, acc[m][2] + b); o.w = act_fn(actfn, acc[m][3] + b);
-            *reinterpret_cast<float4*>(act + (og * TM + m) * ROLLOUT_THREADS + 4 * lane) = o;
-        }
-        __syncthreads();
-        // hidden layers: Linear -> LayerNorm (unbiased std, eps on std) -> activation
-        for (int l = 0; l < L; ++l) {
-            const float* Wt = hid + (size_t)l * (H * H + 3 * H);
-            const float* bb = Wt + H * H;
-            const float* gamma = bb + H;
-            const float* beta = gamma + H;
-            gemm_tile<H>(Wt, act, H, og, lane, acc);
-            float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int m = 0; m < TM; ++m) {
-                const float b = bb[og * TM + m];
-                acc[m][0] += b; acc[m][1] += b; acc[m][2] += b; acc[m][3] += b;
-                s.x += acc[m][0]; s.y += acc[m][1]; s.z += acc[m][2]; s.w += acc[m][3];
-            }
-            *reinterpret_cast<float4*>(part + og * ROLLOUT_THREADS + 4 * lane) = s;
-            __syncthreads();                              // partial sums visible; all reads of act are done
-            float mean[4];
-            {
-                const float4 p0 = *reinterpret_cast<const float4*>(part + 4 * lane);
-                const float4 p1 = *reinterpret_cast<const float4*>(part + ROLLOUT_THREADS + 4 * lane);
-                const float4 p2 = *reinterpret_cast<const float4*>(part + 2 * ROLLOUT_THREADS + 4 * lane);
-                const float4 p3 = *reinterpret_cast<const float4*>(part + 3 * ROLLOUT_THREADS + 4 * lane);
-                mean[0] = (((p0.x + p1.x) + p2.x) + p3.x) / (float)H;
-                mean[1] = (((p0.y + p1.y) + p2.y) + p3.y) / (float)H;
-                mean[2] = (((p0.z + p1.z) + p2.z) + p3.z) / (float)H;
-                mean[3] = (((p0.w + p1.w) + p2.w) + p3.w) / (float)H;
-            }
-            float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int m = 0; m < TM; ++m) {
-                acc[m][0] -= mean[0]; acc[m][1] -= mean[1]; acc[m][2] -= mean[2]; acc[m][3] -= mean[3];
-                q.x = fmaf(acc[m][0], acc[m][0], q.x); q.y = fmaf(acc[m][1], acc[m][1], q.y);
-                q.z = fmaf(acc[m][2], acc[m][2], q.z); q.w = fmaf(acc[m][3], acc[m][3], q.w);
-            }
-            float* part2 = part + 4 * ROLLOUT_THREADS;
-            *reinterpret_cast<float4*>(part2 + og * ROLLOUT_THREADS + 4 * lane) = q;
-            __syncthreads();
-            float den[4];
-            {
-                const float4 p0 = *reinterpret_cast<const float4*>(part2 + 4 * lane);
-                const float4 p1 = *reinterpret_cast<const float4*>(part2 + ROLLOUT_THREADS + 4 * lane);
-                const float4 p2 = *reinterpret_cast<const float4*>(part2 + 2 * ROLLOUT_THREADS + 4 * lane);
-                const float4 p3 = *reinterpret_cast<const float4*>(part2 + 3 * ROLLOUT_THREADS + 4 * lane);
-                den[0] = sqrtf((((p0.x + p1.x) + p2.x) + p3.x) / (float)(H - 1)) + 1e-6f;
-                den[1] = sqrtf((((p0.y + p1.y) + p2.y) + p3.y) / (float)(H - 1)) + 1e-6f;
-                den[2] = sqrtf((((p0.z + p1.z) + p2.z) + p3.z) / (float)(H - 1)) + 1e-6f;
-                den[3] = sqrtf((((p0.w + p1.w) + p2.w) + p3.w) / (float)(H - 1)) + 1e-6f;
-            }
-#pragma unroll
-            for (int m = 0; m < TM; ++m) {
-                const float g = gamma[og * TM + m], be = beta[og * TM + m];
-                float4 o;
-                o.x = act_fn(actfn, g * acc[m][0] / den[0] + be); o.y = act_fn(actfn, g * acc[m][1] / den[1] + be);
-                o.z = act_fn(actfn, g * acc[m][2] / den[2] + be); o.w = act_fn(actfn, g * acc[m][3] / den[3] + be);
-                *reinterpret_cast<float4*>(act + (og * TM + m) * ROLLOUT_THREADS + 4 * lane) = o;
-            }
-            __syncthreads();
-        }
-        // output layer: each thread finishes its own env
-#pragma unroll
-        for (int j = 0; j < A; ++j) {
-            float s0 = 0.f, s1 = 0.f;
-#pragma unroll 4
-            for (int k = 0; k < H; k += 2) {
-                s0 = fmaf(Wo[j * H + k], act[k * ROLLOUT_THREADS + tid], s0);
-                s1 = fmaf(Wo[j * H + k + 1], act[(k + 1) * ROLLOUT_THREADS + tid], s1);
-            }
-            a[j] = tanhf((s0 + s1) + bo[j]);
-        }
+    while (__any_sync(0xffffffffu, !e.done)) {
+        actor_forward_warp<H>(w, L, ar.sh.activation, lane, obs, a);
         if (!e.done) env_step(e, ar, traj, a, obs);
-        if (!__syncthreads_or(e.done ? 0 : 1)) break;      // also orders the act reads above before the next obs write
     }
     if (valid) {
         ar.returns[traj] = e.ret;
@@ -522,12 +538,15 @@ extern "C" int64_t serl_actor_num_params(const serl_actor_shape* s)
 
 static int g_force_simple = -1;
 
-template <int H>
-static cudaError_t launch_gemm(const RolloutArgs& ar, dim3 grid, size_t smem, cudaStream_t s)
+template <int H, int APC>
+static cudaError_t launch_warp(const RolloutArgs& ar, cudaStream_t s)
 {
-    cudaError_t e = cudaFuncSetAttribute(rollout_kernel_gemm<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int P4 = (ar.P + 3) & ~3;
+    const size_t smem = (size_t)PT_TOTAL * 8 + (size_t)APC * P4 * 4;
+    cudaError_t e = cudaFuncSetAttribute(rollout_kernel_warp<H, APC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    rollout_kernel_gemm<H><<<grid, ROLLOUT_THREADS, smem, s>>>(ar);
+    dim3 grid((ar.n_envs + ROLLOUT_THREADS - 1) / ROLLOUT_THREADS, (ar.pop + APC - 1) / APC);
+    rollout_kernel_warp<H, APC><<<grid, ROLLOUT_THREADS * APC, smem, s>>>(ar);
     return cudaGetLastError();
 }
 
@@ -552,18 +571,20 @@ extern "C" int serl_rollout(const float* d_weights, int32_t pop, const serl_acto
     RolloutArgs ar;
     ar.weights = d_weights; ar.P = (int)serl_actor_num_params(shape); ar.sh = *shape;
     ar.ref_levels = d_ref_levels; ar.ref_starts = d_ref_starts; ar.env_mode = d_env_mode; ar.n_envs = n_envs; ar.horizon = horizon;
-    ar.action_noise = d_action_noise; ar.returns = d_returns; ar.steps = d_steps; ar.trace = d_trace;
+    ar.action_noise = d_action_noise; ar.returns = d_returns; ar.steps = d_steps; ar.trace = d_trace; ar.pop = pop;
     const int P4 = (ar.P + 3) & ~3;
     const int H = shape->hidden;
     dim3 grid((n_envs + ROLLOUT_THREADS - 1) / ROLLOUT_THREADS, pop);
     cudaError_t e;
-    const size_t smem_gemm = (size_t)P4 * 4 + (size_t)H * ROLLOUT_THREADS * 4 + 8 * ROLLOUT_THREADS * 4;
-    const bool gemm_ok = !g_force_simple && (H == 32 || H == 64 || H == 72 || H == 96) && smem_gemm <= 227 * 1024;
-    if (gemm_ok) {
-        if (H == 32) e = launch_gemm<32>(ar, grid, smem_gemm, s);
-        else if (H == 64) e = launch_gemm<64>(ar, grid, smem_gemm, s);
-        else if (H == 72) e = launch_gemm<72>(ar, grid, smem_gemm, s);
-        else e = launch_gemm<96>(ar, grid, smem_gemm, s);
+    const bool warp_ok = !g_force_simple && (H == 32 || H == 64 || H == 72 || H == 96) &&
+                         (size_t)PT_TOTAL * 8 + (size_t)P4 * 4 <= 227 * 1024;
+    if (warp_ok) {
+        // two actors per CTA (8 autonomous warps) when two genomes + the plant tables fit in shared memory
+        const bool two = (size_t)PT_TOTAL * 8 + 2ull * P4 * 4 <= 227 * 1024 && pop > 1;
+        if (H == 32) e = two ? launch_warp<32, 2>(ar, s) : launch_warp<32, 1>(ar, s);
+        else if (H == 64) e = two ? launch_warp<64, 2>(ar, s) : launch_warp<64, 1>(ar, s);
+        else if (H == 72) e = two ? launch_warp<72, 2>(ar, s) : launch_warp<72, 1>(ar, s);
+        else e = two ? launch_warp<96, 2>(ar, s) : launch_warp<96, 1>(ar, s);
     } else {
         const size_t smem = (size_t)P4 * 4 + 2ull * H * ROLLOUT_THREADS * 4;
         if (smem > 227 * 1024) return serl_fail(SERL_ERR_UNSUPPORTED, "serl_rollout: genome + activations exceed 227 KB of shared memory");

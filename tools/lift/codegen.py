@@ -79,7 +79,12 @@ class Emitter:
         if k not in self.idx:
             iv = 'i%d' % len(self.idx)
             dv = 'd%d' % len(self.idx)
-            self.lines.append('const int %s = plant_index(PLANT_TAB(%s), %d, %s);' % (iv, axis, n, self.ref(unode)))
+            # rt_GetLookupIndex (@0xf470) as a branch-free count of interior breakpoints below the input:
+            # idx = #{1 <= j <= n-2 : x[j] < u}, with the reference's tie rule (u >= 0: x[i] < u <= x[i+1];
+            # u < 0: x[i] <= u < x[i+1]) folded per breakpoint: a negative breakpoint compares with <=.
+            xs = self.tabs[axis]
+            terms = ['(%s %s %s)' % (hexf(xs[j]), '<=' if xs[j] < 0 else '<', self.ref(unode)) for j in range(1, n - 1)]
+            self.lines.append('const int %s = %s;' % (iv, ' + '.join(terms) if terms else '0'))
             self.lines.append('const %s %s = %s - PLANT_TAB(%s)[%s];' % (self.real, dv, self.ref(unode), axis, iv))
             self.idx[k] = (iv, dv)
         return self.idx[k]
