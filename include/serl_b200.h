@@ -71,6 +71,14 @@ int serl_rollout(const float* d_weights, int32_t pop, const serl_actor_shape* sh
                  double* d_returns, int32_t* d_steps, double* d_fitness, double* d_trace,
                  void* stream);
 
+/* Native plant, batched (replaces envs/<variant>/citation.py:65-72 initialize()/step() for n independent models).
+ * d_X [n,19] f64 continuous states (rtX order: p q r V alpha beta phi theta psi h x_e y_e | washout | 2 params | N1 N1 N2 N2);
+ * d_variant [n] SERL_PLANT_*.  serl_plant_init writes the initial condition of initialize(); serl_plant_step advances
+ * every model by one 0.01 s major step (ode5) with the first three inputs d_cmd [n,3] (de, da, dr; inputs 3..9 = 0).
+ * psi, x_e, y_e are not integrated (they never feed back) and keep their initial values. */
+int serl_plant_init(double* d_X, const int32_t* d_variant, int32_t n, void* stream);
+int serl_plant_step(double* d_X, const double* d_cmd, const int32_t* d_variant, int32_t n, void* stream);
+
 /* ---- neuro-evolution (base/core/mod_neuro_evo.py, classic operators) -------------------------------------
  * All random draws are made on the host in the reference's order; the device applies compact op lists.
  * Launches issued on one stream execute in order; a caller must put ops with a write-after-write or

@@ -1,0 +1,72 @@
+"""Mirror of base/core/mod_neuro_evo.py SSNE (:14-543) on top of the device kernels K2-K5 (serl_b200/evo.py).
+
+Same constructor and `epoch(pop, fitness_evals, bcs_evals=None) -> int` contract; `pop` must be the engine's
+PopulationList (its genomes are mutated in place on the GPU).  Only the classic operators are implemented; asking for
+proximal / safe mutation or distillation crossover raises, as the reference does for unknown operators (:38, :507).
+"""
+import numpy as np
+import torch
+
+from .. import evo
+
+
+class SSNE:
+    def __init__(self, args, critic, evaluate):
+        self.current_gen = 0
+        self.args = args
+        self.critic = critic
+        self.population_size = self.args.pop_size
+        self.num_elitists = max(int(self.args.elite_fraction * args.pop_size), 1)
+        self.evaluate = evaluate
+        self.rl_policy = None
+        self.selection_stats = {'elite': 0, 'selected': 0, 'discarded': 0, 'total': 0.0000001}
+        if self.args.mut_type in ('normal', 'inplace'):
+            self.mutate = None       # classic mutation runs inside epoch() (K5)
+        elif self.args.mut_type in ('proximal', 'safe'):
+            raise NotImplementedError("mut_type '%s' needs per-actor replay buffers + autograd (SURVEY.md 8(f) N3); "
+                                      "use -mut_type normal" % self.args.mut_type)
+        else:
+            raise ValueError('Mutation type is unknown!')
+        if getattr(self.args, 'distil_crossover', False):
+            raise NotImplementedError('distillation crossover is not part of the B200 hot path (SURVEY.md 8(f) N3)')
+        self.last_plan = None
+
+    def _selection_bookkeeping(self, elitist_index, offsprings, unselects):
+        # mod_neuro_evo.py:478-485
+        if self.rl_policy is not None:
+            self.selection_stats['total'] += 1.0
+            if self.rl_policy in elitist_index:
+                self.selection_stats['elite'] += 1.0
+            elif self.rl_policy in offsprings:
+                self.selection_stats['selected'] += 1.0
+            elif self.rl_policy in unselects:
+                self.selection_stats['discarded'] += 1.0
+            self.rl_policy = None
+
+    def epoch(self, pop, fitness_evals, bcs_evals=None):
+        genomes = getattr(pop, 'genomes', None)
+        if genomes is None:
+            raise TypeError('SSNE.epoch needs the engine population (serl_b200.population.PopulationList)')
+        elite, plan = evo.epoch_flat(genomes, fitness_evals, pop.shape_tuple,
+                                     elite_fraction=self.args.elite_fraction, mutation_prob=self.args.mutation_prob,
+                                     mutation_mag=self.args.mutation_mag, selection=self._selection_bookkeeping)
+        self.last_plan = plan
+        # clone() also copies the per-agent replay buffers (:377-382); host-side bookkeeping, in the reference's order
+        for wave in plan.clone_waves:
+            for src, dst in wave:
+                _copy_buffers(pop[int(src)], pop[int(dst)])
+        for desc, _ in plan.cross_waves:
+            for g1, g2, s1, s2, _, _ in desc:
+                _copy_buffers(pop[int(s1)], pop[int(g1)])
+                _copy_buffers(pop[int(s2)], pop[int(g2)])
+        self.current_gen += 1
+        return elite
+
+
+def _copy_buffers(master, replacee):
+    if master is replacee:
+        return
+    replacee.buffer.reset()
+    replacee.buffer.add_content_of(master.buffer)
+    replacee.critical_buffer.reset()
+    replacee.critical_buffer.add_content_of(master.critical_buffer)

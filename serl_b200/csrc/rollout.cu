@@ -529,6 +529,46 @@ __global__ void fitness_mean_kernel(const double* __restrict__ returns, int pop,
     fitness[a] = s / (double)n_envs;
 }
 
+// batched native-plant step: X[n,19] advanced in place by one major step with command cmd[n,3] (inputs 3..9 are 0)
+__global__ void plant_step_kernel(double* __restrict__ X, const double* __restrict__ cmd, const int* __restrict__ variant, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double x[NX], u[3];
+#pragma unroll
+    for (int k = 0; k < NX; ++k) x[k] = X[(size_t)i * NX + k];
+    u[0] = cmd[3 * i]; u[1] = cmd[3 * i + 1]; u[2] = cmd[3 * i + 2];
+    plant_step(variant[i] & 0xff, x, u, plant_tables_blob);
+#pragma unroll
+    for (int k = 0; k < NX; ++k) X[(size_t)i * NX + k] = x[k];
+}
+
+__global__ void plant_ic_kernel(double* __restrict__ X, const int* __restrict__ variant, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double* ic = plant_ic(variant[i] & 0xff);
+    for (int k = 0; k < NX; ++k) X[(size_t)i * NX + k] = ic[k];
+}
+
+extern "C" int serl_plant_init(double* d_X, const int32_t* d_variant, int32_t n, void* stream)
+{
+    if (!d_X || !d_variant || n <= 0) return serl_fail(SERL_ERR_ARG, "serl_plant_init: bad argument");
+    plant_ic_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_X, d_variant, n);
+    serl_count_launch();
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? SERL_OK : serl_fail_cuda(e, "plant_ic_kernel");
+}
+
+extern "C" int serl_plant_step(double* d_X, const double* d_cmd, const int32_t* d_variant, int32_t n, void* stream)
+{
+    if (!d_X || !d_cmd || !d_variant || n <= 0) return serl_fail(SERL_ERR_ARG, "serl_plant_step: bad argument");
+    plant_step_kernel<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(d_X, d_cmd, d_variant, n);
+    serl_count_launch();
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? SERL_OK : serl_fail_cuda(e, "plant_step_kernel");
+}
+
 extern "C" int64_t serl_actor_num_params(const serl_actor_shape* s)
 {
     if (!s) return -1;

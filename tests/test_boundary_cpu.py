@@ -1,0 +1,96 @@
+"""Host logic of the drop-in boundary that needs no GPU: genome views, checkpoint keys, sharding, fitness all-gather (gloo)."""
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from oracle import actor as OA
+
+
+def make_args(pop=4, hidden=8):
+    from serl_b200.parameters import Parameters
+    cla = types.SimpleNamespace(env='PHlab_attitude_nominal', seed=7, pop_size=pop, mut_type='normal')
+    os.makedirs('/tmp/serl_test', exist_ok=True)
+    cwd = os.getcwd(); os.chdir('/tmp/serl_test')
+    try:
+        args = Parameters(cla)
+    finally:
+        os.chdir(cwd)
+    args.device = torch.device('cpu')
+    args.state_dim, args.action_dim, args.hidden_size = 7, 3, hidden
+    return args
+
+
+def test_population_views_and_reference_init_order():
+    from serl_b200.population import PopulationList
+    args = make_args()
+    torch.manual_seed(7)
+    pop = PopulationList(args, device='cpu')
+    torch.manual_seed(7)
+    ref = [OA.Actor(hidden=8) for _ in range(4)]
+    for a, r in zip(pop, ref):
+        assert np.array_equal(a.actor.flat().numpy(), OA.flatten(r))        # same RNG consumption as Actor(args) x pop
+    assert list(pop[0].actor.state_dict().keys())[:4] == ['net.0.weight', 'net.0.bias', 'net.2.weight', 'net.2.bias']
+    assert 'net.3.gamma' in pop[0].actor.state_dict() and 'net.11.bias' in pop[0].actor.state_dict()
+    # parameters are views of the genome matrix, both ways
+    pop.genomes[2, 0] = 123.0
+    assert pop[2].actor.net[0].weight.data[0, 0].item() == 123.0
+    pop[1].actor.net[11].bias.data[2] = -5.0
+    assert pop.genomes[1, -1].item() == -5.0
+    obs = np.zeros(7)
+    assert pop[0].actor.select_action(obs).shape == (3,)
+
+
+def test_ssne_rejects_out_of_scope_operators():
+    from serl_b200.core.mod_neuro_evo import SSNE
+    args = make_args()
+    args.mut_type = 'proximal'
+    with pytest.raises(NotImplementedError):
+        SSNE(args, None, None)
+    args.mut_type = 'bogus'
+    with pytest.raises(ValueError):
+        SSNE(args, None, None)
+
+
+def test_select_env_names():
+    from serl_b200.envs import config
+    e = config.select_env('PHlab_attitude_nominal')
+    assert e.action_space.shape[0] == 3 and e.observation_space.shape[0] == 7
+    assert config.select_env('phlab_attitude_ice').variant == 'ice'
+    assert config.select_env('phlab_attitude_be').fault == 'be'
+    with pytest.raises(ValueError):
+        config.select_env('phlab_attitude_bogus')
+    with pytest.raises(ValueError):
+        config.select_env('cartpole')
+
+
+def test_shard_bounds_cover_population():
+    from serl_b200 import engine
+    for pop in (1, 7, 10, 512, 513):
+        for world in (1, 2, 3, 8):
+            b = [engine.shard_bounds(pop, world, r) for r in range(world)]
+            assert b[0][0] == 0 and b[-1][1] == pop
+            assert all(b[i][1] == b[i + 1][0] for i in range(world - 1))
+
+
+def _worker(rank, world, port, pop, out):
+    import torch.distributed as dist
+    from serl_b200 import engine
+    dist.init_process_group('gloo', init_method='tcp://127.0.0.1:%d' % port, rank=rank, world_size=world)
+    full = torch.arange(pop, dtype=torch.float64) * 1.5 - 3.0
+    lo, hi = engine.shard_bounds(pop, world, rank)
+    got = engine.gather_fitness(full[lo:hi].clone(), pop, world, rank)
+    out[rank] = bool(torch.equal(got, full))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('pop', [7, 10])
+def test_fitness_all_gather_world2_gloo(pop):
+    mgr = mp.Manager()
+    out = mgr.dict()
+    port = 29500 + (os.getpid() + pop) % 2000
+    mp.spawn(_worker, args=(2, port, pop, out), nprocs=2, join=True)
+    assert out[0] and out[1]

@@ -1,0 +1,128 @@
+"""The reference-facing surface on the GPU: batched plant C-ABI, CitationEnv per-step API, Agent.evaluate / train."""
+import ctypes
+import os
+import random
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import actor as OA, phlab, plant as OP
+
+pytestmark = pytest.mark.gpu
+
+
+def make_args(pop=6, hidden=16, **kw):
+    from serl_b200.parameters import Parameters
+    cla = types.SimpleNamespace(env='PHlab_attitude_nominal', seed=7, pop_size=pop, mut_type='normal', test_ea=True, **kw)
+    os.makedirs('/tmp/serl_test', exist_ok=True)
+    cwd = os.getcwd(); os.chdir('/tmp/serl_test')
+    try:
+        args = Parameters(cla)
+    finally:
+        os.chdir(cwd)
+    args.save_foldername = '/tmp/serl_test/'
+    args.state_dim, args.action_dim, args.hidden_size = 7, 3, hidden
+    return args
+
+
+@pytest.mark.parametrize('variant', ['h2000_v90', 'ice', 'cg'])
+def test_plant_step_kernel_matches_oracle(variant):
+    from serl_b200 import _native, rollout
+    L = _native.lib()
+    dev = torch.device('cuda:0')
+    n = 5
+    v = torch.full((n,), rollout.PLANT_VARIANTS.index(variant), dtype=torch.int32, device=dev)
+    X = torch.empty((n, 19), dtype=torch.float64, device=dev)
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _native.check(L.serl_plant_init(ctypes.c_void_p(X.data_ptr()), ctypes.c_void_p(v.data_ptr()), n, st), 'init')
+    pl = OP.PortPlant(variant)
+    assert np.array_equal(X.cpu().numpy()[0], pl.initial_state())
+    rng = np.random.RandomState(0)
+    Xo = [pl.initial_state() for _ in range(n)]
+    live = [0, 1, 2, 3, 4, 5, 6, 7, 9, 12, 15, 16, 17, 18]
+    for k in range(200):
+        cmd = 0.08 * rng.uniform(-1, 1, (n, 3))
+        d = torch.as_tensor(cmd, device=dev)
+        _native.check(L.serl_plant_step(ctypes.c_void_p(X.data_ptr()), ctypes.c_void_p(d.data_ptr()), ctypes.c_void_p(v.data_ptr()), n, st), 'step')
+        for i in range(n):
+            _, Xo[i] = pl.step(Xo[i], np.concatenate([cmd[i], np.zeros(7)]))
+    got = X.cpu().numpy()
+    ref = np.array(Xo)
+    # same operation order in fp64; only libm (sin/cos/pow/exp: CUDA vs glibc, <= 2 ulp) differs
+    assert np.abs(got[:, live] - ref[:, live]).max() < 1e-9
+    assert np.allclose(got[:, live], ref[:, live], rtol=1e-11, atol=1e-12)
+
+
+def test_citation_env_step_api_matches_oracle_env():
+    from serl_b200.envs import config
+    env = config.select_env('PHlab_attitude_nominal')
+    np.random.seed(5)
+    obs = env.reset()
+    o_env = phlab.CitationEnv('nominal', 'auto')
+    o_obs = o_env.reset(env.levels, env.starts)
+    assert np.allclose(obs, o_obs)
+    act = OA.unflatten(np.load(os.path.join(os.path.dirname(__file__), 'golden', 'actors.npz'))['serl10_elite_h72_tanh'], hidden=72)
+    for k in range(150):
+        a = act.select_action(o_obs)
+        obs, r, d, info = env.step(a)
+        o_obs, o_r, o_d, o_info = o_env.step(a)
+        assert d == o_d and abs(r - o_r) < 1e-9 and np.abs(obs - o_obs).max() < 1e-9
+    assert abs(info['t'] - o_info['t']) < 1e-12
+
+
+def test_agent_evaluate_returns_reference_shaped_episode():
+    from serl_b200.core import agent as agent_mod
+    from serl_b200.envs import config
+    args = make_args(pop=4, hidden=72)
+    env = config.select_env('PHlab_attitude_nominal')
+    torch.manual_seed(7); np.random.seed(7); random.seed(7)
+    ag = agent_mod.Agent(args, env)
+    w = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'actors.npz'))['serl10_pop_h72_tanh']
+    ag.pop.genomes.copy_(torch.as_tensor(w[:4]))
+    np.random.seed(11)
+    ag.gen_frames = 0
+    ep = ag.evaluate(ag.pop[1], is_action_noise=False, store_transition=False)
+    np.random.seed(11)
+    levels, starts = env.draw_reference()
+    o = phlab.run_episode(phlab.CitationEnv('nominal', 'auto'), OA.unflatten(w[1], hidden=72), levels, starts, record=True)
+    assert len(ep.reward_lst) == o['steps'] == len(ep.state_history)
+    assert abs(ep.fitness - o['fitness']) <= 1e-4 * abs(o['fitness'])
+    assert abs(ep.length - o['t']) < 1e-12
+    assert ep.actions.shape == (o['steps'], 3)
+    assert ep.get_history().shape == (o['steps'], 19)
+    # exploration episode stores transitions and keeps the np.random stream where the reference would leave it
+    np.random.seed(3)
+    ep2 = ag.evaluate(ag.rl_agent, is_action_noise=True, store_transition=True)
+    n = len(ep2.reward_lst)
+    after = np.random.rand()
+    np.random.seed(3); env.draw_reference(); np.random.randn(n, 3)
+    assert after == np.random.rand()
+    assert len(ag.replay_buffer) == n and ag.num_frames == n
+
+
+def test_agent_train_generations_and_checkpoint_format():
+    from serl_b200.core import agent as agent_mod
+    from serl_b200.envs import config
+    args = make_args(pop=6, hidden=16)
+    env = config.select_env('PHlab_attitude_nominal')
+    torch.manual_seed(7); np.random.seed(7); random.seed(7)
+    ag = agent_mod.Agent(args, env)
+    before = ag.pop.genomes.clone()
+    keys = {'best_train_fitness', 'test_score', 'test_sd', 'pop_avg', 'pop_min', 'elite_index', 'avg_smoothness', 'smoothness_sd',
+            'rl_reward', 'rl_smoothness', 'rl_smoothness_std', 'rl_std', 'avg_ep_len', 'ep_len_sd', 'PG_obj', 'TD_loss', 'pop_novelty'}
+    for gen in range(2):
+        stats = ag.train()
+        assert set(stats.keys()) == keys          # agent.py:297-315
+        assert np.isfinite(stats['best_train_fitness']) and stats['pop_min'] <= stats['pop_avg'] <= stats['best_train_fitness']
+        assert 0 <= stats['elite_index'] < 6
+    assert not torch.equal(before, ag.pop.genomes)
+    assert ag.num_frames > 0 and ag.num_episodes > 0
+    assert set(ag.evolver.selection_stats) == {'elite', 'selected', 'discarded', 'total'} and ag.evolver.selection_stats['total'] >= 1
+    ag.save_agent(args, stats['elite_index'])
+    pop_dict = torch.load('/tmp/serl_test/evo_nets.pkl', weights_only=False)
+    assert sorted(pop_dict) == ['actor_%d' % i for i in range(6)]
+    assert list(pop_dict['actor_0'])[:2] == ['net.0.weight', 'net.0.bias']
+    oracle_actor = OA.from_state_dict(torch.load('/tmp/serl_test/elite_net.pkl', weights_only=False), 'tanh')   # loads into the reference layout
+    assert np.array_equal(OA.flatten(oracle_actor), ag.pop.genomes[int(stats['elite_index'])].cpu().numpy())
