@@ -99,13 +99,31 @@ def _cpu_worker(args):
     return steps, time.perf_counter() - t0
 
 
+def host_cores():
+    """usable host cores: os.cpu_count() capped by the cgroup CPU quota (the GPU boxes expose 128 CPUs but grant 16)."""
+    n = os.cpu_count() or 1
+    try:
+        q, per = open('/sys/fs/cgroup/cpu.max').read().split()
+        if q != 'max':
+            n = max(1, min(n, int(int(q) / int(per))))
+    except Exception:
+        pass
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    return n
+
+
 def cpu_reference_throughput(n_episodes_per_core=1, cores=None):
     """The reference's CPU execution model (one process per core, each with its own copy of the native plant binary,
     batch-1 torch forward, numpy wrapper) on a bounded sample of the bench workload."""
     import multiprocessing as mp
     from oracle import refsig, build as ob
     ob.build()
-    cores = cores or os.cpu_count()
+    cores = cores or host_cores()
+    os.environ.setdefault('OMP_NUM_THREADS', '1')
+    os.environ.setdefault('MKL_NUM_THREADS', '1')
     w = population(8)
     lv, st = refsig.make_ref_params(8)
     jobs = [[((c * n_episodes_per_core + i) % 8, (c + i) % 8) for i in range(n_episodes_per_core)] for c in range(cores)]
@@ -221,13 +239,18 @@ def run_ours(args):
     h2d = w_host.numel() * 4 + lv_host.numel() * 8 + st_host.numel() * 8 + md_host.numel() * 4
     d2h = fit_host.numel() * 8
 
+    from serl_b200 import engine
+
     def e2e_step(res):
+        # the call a user makes: host genomes + env parameters in, fitness out (engine.evaluate_population is what
+        # Agent.train uses); H2D of this rank's inputs and D2H of the gathered fitness are inside the timed region
         w.copy_(w_host, non_blocking=True)
         lv.copy_(lv_host, non_blocking=True)
         st.copy_(st_host, non_blocking=True)
         md.copy_(md_host, non_blocking=True)
-        r = one_step(res)
-        fit_host.copy_(r.fitness, non_blocking=True)
+        r = rollout.population_rollout(w, sh, lv, st, md, horizon=HORIZON, out=res)
+        fit = engine.gather_fitness(r.fitness, world * POP, world, rank) if world > 1 else r.fitness
+        fit_host.copy_(fit[rank * POP:(rank + 1) * POP], non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return r
 

@@ -29,6 +29,9 @@ class Agent:
     def __init__(self, args, environment):
         self.args = args
         self.env = environment
+        if not torch.cuda.is_available():
+            from .._native import NativeError
+            raise NativeError('serl_b200.Agent needs a CUDA device: the rollout / evolution engine has no CPU fallback')
         self.device = torch.device('cuda', torch.cuda.current_device())
         self.pop = PopulationList(args, self.device) if args.pop_size else []
         self.rl_agent = td3.TD3(args)
