@@ -27,8 +27,11 @@ typedef double real;
 #define PLANT_LOG10 log10
 #define PLANT_POW pow
 #define PLANT_XARGS
+#define PLANT_CONSTS(n) static const double plant_k[n]
+#define PLANT_K(i) plant_k[i]
 #include "plant_support.h"
 #include "gen/plant_tables.h"
+#include "gen/plant_consts.h"
 #include "gen/plant_rhs_h2000_v90.h"
 #include "gen/plant_rhs_ice.h"
 #include "gen/plant_rhs_cg.h"

@@ -44,6 +44,9 @@ typedef double real;
 #undef PLANT_FN
 #define PLANT_FN static __device__ __noinline__
 #include "gen/plant_tables_blob.h"
+#define PLANT_CONSTS(n) static __constant__ double plant_k[n]
+#define PLANT_K(i) plant_k[i]
+#include "gen/plant_consts.h"
 #include "gen/plant_rhs_h2000_v90.h"
 #include "gen/plant_rhs_ice.h"
 #include "gen/plant_rhs_cg.h"
@@ -327,37 +330,42 @@ rollout_kernel_simple(RolloutArgs ar)
 // The activation of neuron k for env 4g+c lives in lane (g, og = k/TM), register in[k%TM][c]; the next layer
 // fetches it with one shuffle per (k, c).  Reductions over neurons are xor-butterflies over the two og bits, so
 // the four lanes of a group hold bit-identical means / deviations.
+// All MLP arithmetic uses the packed FP32 FMA of sm_100 (FFMA2: two IEEE-rn fmas per issued instruction); a float2
+// register pair holds two consecutive output neurons (m, m+1) of one env, exactly what one LDS.64 of the transposed
+// weight row delivers, and the activation of the source neuron is broadcast into both halves.
 template <int H>
-__device__ __forceinline__ void warp_layer(const float* __restrict__ Wt, const float (&in)[H / 4][4], float (&acc)[H / 4][4],
+__device__ __forceinline__ void warp_layer(const float* __restrict__ Wt, const float2 (&in)[H / 8][4], float2 (&acc)[H / 8][4],
                                            int og, int lane)
 {
-    constexpr int TM = H / 4;
+    constexpr int TM = H / 4, TM2 = H / 8;
 #pragma unroll
-    for (int m = 0; m < TM; ++m)
+    for (int m = 0; m < TM2; ++m)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) acc[m][c] = 0.f;
+        for (int c = 0; c < 4; ++c) acc[m][c] = make_float2(0.f, 0.f);
     const int gbase = lane & ~3;
 #pragma unroll 1
     for (int so = 0; so < 4; ++so) {
         const float* wrow = Wt + (size_t)(so * TM) * H + og * TM;
 #pragma unroll
         for (int m = 0; m < TM; ++m) {
-            const float a0 = __shfl_sync(0xffffffffu, in[m][0], gbase + so);
-            const float a1 = __shfl_sync(0xffffffffu, in[m][1], gbase + so);
-            const float a2 = __shfl_sync(0xffffffffu, in[m][2], gbase + so);
-            const float a3 = __shfl_sync(0xffffffffu, in[m][3], gbase + so);
+            // activation of source neuron k = so*TM + m for the four envs of this group
+            const float src0 = (m & 1) ? in[m >> 1][0].y : in[m >> 1][0].x;
+            const float src1 = (m & 1) ? in[m >> 1][1].y : in[m >> 1][1].x;
+            const float src2 = (m & 1) ? in[m >> 1][2].y : in[m >> 1][2].x;
+            const float src3 = (m & 1) ? in[m >> 1][3].y : in[m >> 1][3].x;
+            const float a0 = __shfl_sync(0xffffffffu, src0, gbase + so);
+            const float a1 = __shfl_sync(0xffffffffu, src1, gbase + so);
+            const float a2 = __shfl_sync(0xffffffffu, src2, gbase + so);
+            const float a3 = __shfl_sync(0xffffffffu, src3, gbase + so);
+            const float2 b0 = make_float2(a0, a0), b1 = make_float2(a1, a1), b2 = make_float2(a2, a2), b3 = make_float2(a3, a3);
             const float2* wp = reinterpret_cast<const float2*>(wrow + m * H);
 #pragma unroll
-            for (int m2 = 0; m2 < TM / 2; ++m2) {
+            for (int m2 = 0; m2 < TM2; ++m2) {
                 const float2 w2 = wp[m2];
-                acc[2 * m2][0] = fmaf(w2.x, a0, acc[2 * m2][0]);
-                acc[2 * m2][1] = fmaf(w2.x, a1, acc[2 * m2][1]);
-                acc[2 * m2][2] = fmaf(w2.x, a2, acc[2 * m2][2]);
-                acc[2 * m2][3] = fmaf(w2.x, a3, acc[2 * m2][3]);
-                acc[2 * m2 + 1][0] = fmaf(w2.y, a0, acc[2 * m2 + 1][0]);
-                acc[2 * m2 + 1][1] = fmaf(w2.y, a1, acc[2 * m2 + 1][1]);
-                acc[2 * m2 + 1][2] = fmaf(w2.y, a2, acc[2 * m2 + 1][2]);
-                acc[2 * m2 + 1][3] = fmaf(w2.y, a3, acc[2 * m2 + 1][3]);
+                acc[m2][0] = __ffma2_rn(w2, b0, acc[m2][0]);
+                acc[m2][1] = __ffma2_rn(w2, b1, acc[m2][1]);
+                acc[m2][2] = __ffma2_rn(w2, b2, acc[m2][2]);
+                acc[m2][3] = __ffma2_rn(w2, b3, acc[m2][3]);
             }
         }
     }
@@ -373,7 +381,7 @@ __device__ __forceinline__ float group_sum(float v)
 template <int H>
 __device__ void actor_forward_warp(const float* __restrict__ w, int L, int actfn, int lane, const float* obs, float* action)
 {
-    constexpr int TM = H / 4;
+    constexpr int TM = H / 4, TM2 = H / 8;
     constexpr int S = 7, A = 3;
     const int og = lane & 3, gbase = lane & ~3;
     const float* Wt0 = w;
@@ -381,30 +389,35 @@ __device__ void actor_forward_warp(const float* __restrict__ w, int L, int actfn
     const float* hid = b0 + H;
     const float* Wo = hid + (size_t)L * (H * H + 3 * H);
     const float* bo = Wo + A * H;
-    float in[TM][4], acc[TM][4];
+    float2 in[TM2][4], acc[TM2][4];
     // input layer: observation of env 4g+c lives in lane gbase+c
 #pragma unroll
-    for (int m = 0; m < TM; ++m)
+    for (int m = 0; m < TM2; ++m)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) acc[m][c] = 0.f;
+        for (int c = 0; c < 4; ++c) acc[m][c] = make_float2(0.f, 0.f);
 #pragma unroll
     for (int k = 0; k < S; ++k) {
         const float a0 = __shfl_sync(0xffffffffu, obs[k], gbase + 0);
         const float a1 = __shfl_sync(0xffffffffu, obs[k], gbase + 1);
         const float a2 = __shfl_sync(0xffffffffu, obs[k], gbase + 2);
         const float a3 = __shfl_sync(0xffffffffu, obs[k], gbase + 3);
+        const float2 b0v = make_float2(a0, a0), b1v = make_float2(a1, a1), b2v = make_float2(a2, a2), b3v = make_float2(a3, a3);
+        const float2* wp = reinterpret_cast<const float2*>(Wt0 + k * H + og * TM);
 #pragma unroll
-        for (int m = 0; m < TM; ++m) {
-            const float wv = Wt0[k * H + og * TM + m];
-            acc[m][0] = fmaf(wv, a0, acc[m][0]); acc[m][1] = fmaf(wv, a1, acc[m][1]);
-            acc[m][2] = fmaf(wv, a2, acc[m][2]); acc[m][3] = fmaf(wv, a3, acc[m][3]);
+        for (int m2 = 0; m2 < TM2; ++m2) {
+            const float2 w2 = wp[m2];
+            acc[m2][0] = __ffma2_rn(w2, b0v, acc[m2][0]); acc[m2][1] = __ffma2_rn(w2, b1v, acc[m2][1]);
+            acc[m2][2] = __ffma2_rn(w2, b2v, acc[m2][2]); acc[m2][3] = __ffma2_rn(w2, b3v, acc[m2][3]);
         }
     }
 #pragma unroll
-    for (int m = 0; m < TM; ++m) {
-        const float b = b0[og * TM + m];
+    for (int m2 = 0; m2 < TM2; ++m2) {
+        const float2 b = *reinterpret_cast<const float2*>(b0 + og * TM + 2 * m2);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) in[m][c] = act_fn(actfn, acc[m][c] + b);
+        for (int c = 0; c < 4; ++c) {
+            in[m2][c].x = act_fn(actfn, acc[m2][c].x + b.x);
+            in[m2][c].y = act_fn(actfn, acc[m2][c].y + b.y);
+        }
     }
     // hidden layers: Linear -> LayerNorm (unbiased std, eps on std; mod_utils.py:47-50) -> activation
 #pragma unroll 1
@@ -416,26 +429,36 @@ __device__ void actor_forward_warp(const float* __restrict__ w, int L, int actfn
         warp_layer<H>(Wt, in, acc, og, lane);
         float s[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int m = 0; m < TM; ++m) {
-            const float b = bb[og * TM + m];
+        for (int m2 = 0; m2 < TM2; ++m2) {
+            const float2 b = *reinterpret_cast<const float2*>(bb + og * TM + 2 * m2);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) { acc[m][c] += b; s[c] += acc[m][c]; }
+            for (int c = 0; c < 4; ++c) {
+                acc[m2][c].x += b.x; s[c] += acc[m2][c].x;
+                acc[m2][c].y += b.y; s[c] += acc[m2][c].y;
+            }
         }
         float mean[4], den[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) mean[c] = group_sum(s[c]) / (float)H;
         float q[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int m = 0; m < TM; ++m)
+        for (int m2 = 0; m2 < TM2; ++m2)
 #pragma unroll
-            for (int c = 0; c < 4; ++c) { acc[m][c] -= mean[c]; q[c] = fmaf(acc[m][c], acc[m][c], q[c]); }
+            for (int c = 0; c < 4; ++c) {
+                acc[m2][c].x -= mean[c]; q[c] = fmaf(acc[m2][c].x, acc[m2][c].x, q[c]);
+                acc[m2][c].y -= mean[c]; q[c] = fmaf(acc[m2][c].y, acc[m2][c].y, q[c]);
+            }
 #pragma unroll
         for (int c = 0; c < 4; ++c) den[c] = sqrtf(group_sum(q[c]) / (float)(H - 1)) + 1e-6f;
 #pragma unroll
-        for (int m = 0; m < TM; ++m) {
-            const float g = gamma[og * TM + m], be = beta[og * TM + m];
+        for (int m2 = 0; m2 < TM2; ++m2) {
+            const float2 g = *reinterpret_cast<const float2*>(gamma + og * TM + 2 * m2);
+            const float2 be = *reinterpret_cast<const float2*>(beta + og * TM + 2 * m2);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) in[m][c] = act_fn(actfn, g * acc[m][c] / den[c] + be);
+            for (int c = 0; c < 4; ++c) {
+                in[m2][c].x = act_fn(actfn, g.x * acc[m2][c].x / den[c] + be.x);
+                in[m2][c].y = act_fn(actfn, g.y * acc[m2][c].y / den[c] + be.y);
+            }
         }
     }
     // output layer: partial dot products over this lane's neurons, reduced over the group; lane og keeps env 4g+og
@@ -443,10 +466,10 @@ __device__ void actor_forward_warp(const float* __restrict__ w, int L, int actfn
     for (int j = 0; j < A; ++j) {
         float p[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int m = 0; m < TM; ++m) {
-            const float wv = Wo[j * H + og * TM + m];
+        for (int m2 = 0; m2 < TM2; ++m2) {
+            const float2 wv = *reinterpret_cast<const float2*>(Wo + j * H + og * TM + 2 * m2);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) p[c] = fmaf(wv, in[m][c], p[c]);
+            for (int c = 0; c < 4; ++c) { p[c] = fmaf(wv.x, in[m2][c].x, p[c]); p[c] = fmaf(wv.y, in[m2][c].y, p[c]); }
         }
 #pragma unroll
         for (int c = 0; c < 4; ++c) p[c] = group_sum(p[c]);

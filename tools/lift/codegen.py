@@ -31,8 +31,37 @@ def tables_text(tabs):
     return '\n'.join(out)
 
 
+class ConstPool:
+    """double literals that do not fit a 32-bit immediate (low word != 0) are pooled into one array (`PLANT_K(i)`): on the
+    device that array lives in constant memory, so DFMA/DMUL/DSETP take them as c[bank][offset] operands instead of
+    materialising every 64-bit literal with two uniform-register moves."""
+
+    def __init__(self):
+        self.index = {}
+        self.vals = []
+
+    def ref(self, x):
+        import struct
+        bits = struct.unpack('<Q', struct.pack('<d', x))[0]
+        if (bits & 0xffffffff) == 0 or x != x:
+            return hexf(x)
+        if bits not in self.index:
+            self.index[bits] = len(self.vals)
+            self.vals.append(x)
+        return 'PLANT_K(%d)' % self.index[bits]
+
+    def text(self):
+        out = ['PLANT_CONSTS(%d) = {' % max(len(self.vals), 1)]
+        vals = self.vals or [0.0]
+        for i in range(0, len(vals), 4):
+            out.append('  ' + ', '.join(hexf(x) for x in vals[i:i + 4]) + ',')
+        out.append('};')
+        return '\n'.join(out)
+
+
 class Emitter:
-    def __init__(self, tracer, real='real'):
+    def __init__(self, tracer, real='real', pool=None):
+        self.pool = pool
         self.tr = tracer
         self.tabs = {}        # name -> list of floats
         self.tabname = {}     # key -> name
@@ -65,12 +94,15 @@ class Emitter:
         return self.tabname[key]
 
     # ---- helpers ----
+    def lit(self, x):
+        return self.pool.ref(x) if self.pool is not None else hexf(x)
+
     def ref(self, a):
         if S.is_sym(a):
             if a.op == 'const':
-                return hexf(S.fval(a.args[0]))
+                return self.lit(S.fval(a.args[0]))
             return 'v%d' % a.id
-        return hexf(S.fval(a))
+        return self.lit(S.fval(a))
 
     def index_of(self, axis_key, unode):
         axis = self.table(axis_key)
@@ -83,7 +115,7 @@ class Emitter:
             # idx = #{1 <= j <= n-2 : x[j] < u}, with the reference's tie rule (u >= 0: x[i] < u <= x[i+1];
             # u < 0: x[i] <= u < x[i+1]) folded per breakpoint: a negative breakpoint compares with <=.
             xs = self.tabs[axis]
-            terms = ['(%s %s %s)' % (hexf(xs[j]), '<=' if xs[j] < 0 else '<', self.ref(unode)) for j in range(1, n - 1)]
+            terms = ['(%s %s %s)' % (self.lit(xs[j]), '<=' if xs[j] < 0 else '<', self.ref(unode)) for j in range(1, n - 1)]
             self.lines.append('const int %s = %s;' % (iv, ' + '.join(terms) if terms else '0'))
             self.lines.append('const %s %s = %s - PLANT_TAB(%s)[%s];' % (self.real, dv, self.ref(unode), axis, iv))
             self.idx[k] = (iv, dv)
