@@ -12,7 +12,7 @@ CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libserl_b200.so')
 SOURCES = ['common.cu', 'rollout.cu', 'evo.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
-              '-Xcompiler', '-fPIC', '-Xptxas', '-v', '--fmad=false']
+              '-Xcompiler', '-fPIC', '-Xptxas', '-v']
 
 
 def _deps():

@@ -35,6 +35,7 @@ typedef double real;
 #define PLANT_FABS fabs
 #define PLANT_SIN sin
 #define PLANT_COS cos
+#define PLANT_SINCOS sincos
 #define PLANT_TAN tan
 #define PLANT_EXP exp
 #define PLANT_LOG10 log10

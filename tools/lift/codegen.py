@@ -60,7 +60,10 @@ class ConstPool:
 
 
 class Emitter:
-    def __init__(self, tracer, real='real', pool=None):
+    def __init__(self, tracer, real='real', pool=None, fast=False):
+        # fast (device build only): divisions by table spacings become multiplications by pre-inverted tables and
+        # sin/cos of the same angle are computed by one sincos; results move by <= 1 ulp per affected operation
+        self.fast = fast
         self.pool = pool
         self.tr = tracer
         self.tabs = {}        # name -> list of floats
@@ -136,6 +139,8 @@ class Emitter:
         L = self.lines
         li = S.Tracer.lookup_index
         cnt = {}
+        partner = {(n.op, n.args[0].id): n.id for n in S.G.nodes if n.id in live and n.op in ('sin', 'cos')}
+        done_pair = set()
         for n in S.G.nodes:
             if n.id not in live or n.op == 'const':
                 continue
@@ -148,6 +153,8 @@ class Emitter:
                 L.append('const %s %s = X[%d];' % (R, v, a[0]))
             elif op == 'U':
                 L.append('const %s %s = U[%d];' % (R, v, a[0]))
+            elif op == 'div' and self.fast and a[1].op == 'const' and S.fval(a[1].args[0]) != 0.0:
+                L.append('const %s %s = %s * %s;' % (R, v, r(a[0]), self.lit(1.0 / S.fval(a[1].args[0]))))   # x / c -> x * (1/c)
             elif op in ('add', 'sub', 'mul', 'div'):
                 sym = {'add': '+', 'sub': '-', 'mul': '*', 'div': '/'}[op]
                 L.append('const %s %s = %s %s %s;' % (R, v, r(a[0]), sym, r(a[1])))
@@ -170,6 +177,12 @@ class Emitter:
                 L.append('const %s %s = %s ? %s : 0.0;' % (R, v, r(a[0]), r(a[1])))
             elif op == 'mandn':
                 L.append('const %s %s = %s ? 0.0 : %s;' % (R, v, r(a[0]), r(a[1])))
+            elif op in ('sin', 'cos') and self.fast and (('cos' if op == 'sin' else 'sin'), a[0].id) in partner:
+                other = partner[('cos' if op == 'sin' else 'sin'), a[0].id]
+                if (op, a[0].id) not in done_pair:
+                    sn, cn = (v, 'v%d' % other) if op == 'sin' else ('v%d' % other, v)
+                    L.append('%s %s, %s; PLANT_SINCOS(%s, &%s, &%s);' % (R, sn, cn, r(a[0]), sn, cn))
+                    done_pair.add((op, a[0].id)); done_pair.add((('cos' if op == 'sin' else 'sin'), a[0].id))
             elif op in ('sin', 'cos', 'tan', 'exp', 'log10'):
                 L.append('const %s %s = PLANT_%s(%s);' % (R, v, op.upper(), r(a[0])))
             elif op == 'pow':
@@ -219,7 +232,11 @@ class Emitter:
                     L.append('const int k%d = %s + %d * %s;' % (n.id, ixv, nx, iyv))
                     L.append('const %s a%d = PLANT_TAB(%s)[k%d] * %s + PLANT_TAB(%s)[k%d];' % (R, n.id, sxn, n.id, dxv, zn, n.id))
                     L.append('const %s b%d = PLANT_TAB(%s)[k%d + %d] * %s + PLANT_TAB(%s)[k%d + %d];' % (R, n.id, sxn, n.id, nx, dxv, zn, n.id, nx))
-                    L.append('const %s %s = (b%d - a%d) / PLANT_TAB(%s)[%s] * %s + a%d;' % (R, v, n.id, n.id, dyn, iyv, dyv, n.id))
+                    if self.fast:
+                        rdyn = self.derived('rdy', [1.0 / d for d in dy])
+                        L.append('const %s %s = (b%d - a%d) * PLANT_TAB(%s)[%s] * %s + a%d;' % (R, v, n.id, n.id, rdyn, iyv, dyv, n.id))
+                    else:
+                        L.append('const %s %s = (b%d - a%d) / PLANT_TAB(%s)[%s] * %s + a%d;' % (R, v, n.id, n.id, dyn, iyv, dyv, n.id))
             elif op == 'table3':
                 k1, k2, k3, k4, u0, u1, u2 = a
                 t = [self.table(k) for k in (k1, k2, k3, k4)]
