@@ -31,11 +31,67 @@ typedef double real;
 #define PLANT_TAB(name) (plant_tab + PT_OFF_##name)
 #define PLANT_XARGS , const double* __restrict__ plant_tab
 #define PLANT_IC(v) static __device__ const double plant_ic_##v[19]
-#define PLANT_SQRT sqrt
+// ---- fast fp64 math for the device plant (<= ~1 ulp; the oracle keeps the reference's exact operations) -------
+// division: 20-bit hardware reciprocal seed + two Newton steps + one residual correction (9 instructions instead of ~33)
+__device__ __forceinline__ double plant_div_fast(double a, double b)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+    double e = fma(-b, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-b, r, 1.0);
+    r = fma(r, e, r);
+    const double q = a * r;
+    return fma(fma(-b, q, a), r, q);
+}
+// sqrt: 20-bit rsqrt seed + two Newton steps + residual correction; zero / negative / non-finite go to the library
+__device__ __forceinline__ double plant_sqrt_fast(double x)
+{
+    if (!(x > 1e-300 && x < 1e300)) return sqrt(x);
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double hx = 0.5 * x;
+    y = y * fma(-hx * y, y, 1.5);
+    y = y * fma(-hx * y, y, 1.5);
+    const double s = x * y;
+    return fma(fma(-s, s, x), 0.5 * y, s);
+}
+// sincos for |x| <= 8 (the plant's angles are bounded by the termination rule): two-term Cody-Waite reduction by pi/2
+// and the fdlibm kernel polynomials; larger arguments fall back to the library.
+__device__ __forceinline__ void plant_sincos_fast(double x, double* sp, double* cp)
+{
+    if (!(fabs(x) <= 8.0)) { sincos(x, sp, cp); return; }
+    const double q = rint(x * 0.6366197723675814);
+    double r = fma(-q, 1.5707963267948966, x);
+    r = fma(-q, 6.123233995736766e-17, r);
+    const double z = r * r;
+    double ps = 1.58969099521155010221e-10;
+    ps = fma(ps, z, -2.50507602534068634195e-08);
+    ps = fma(ps, z, 2.75573137070700676789e-06);
+    ps = fma(ps, z, -1.98412698298579493134e-04);
+    ps = fma(ps, z, 8.33333333332248946124e-03);
+    ps = fma(ps, z, -1.66666666666666324348e-01);
+    const double s = fma(r * z, ps, r);
+    double pc = -1.13596475577881948265e-11;
+    pc = fma(pc, z, 2.08757232129817482790e-09);
+    pc = fma(pc, z, -2.75573143513906633035e-07);
+    pc = fma(pc, z, 2.48015872894767294178e-05);
+    pc = fma(pc, z, -1.38888888888741095749e-03);
+    pc = fma(pc, z, 4.16666666666666019037e-02);
+    const double c = fma(z * z, pc, fma(-0.5, z, 1.0));
+    const int n = (int)q & 3;
+    const double s1 = (n & 1) ? c : s, c1 = (n & 1) ? s : c;
+    *sp = (n & 2) ? -s1 : s1;
+    *cp = ((n + 1) & 2) ? -c1 : c1;
+}
+__device__ __forceinline__ double plant_sin_fast(double x) { double s, c; plant_sincos_fast(x, &s, &c); return s; }
+__device__ __forceinline__ double plant_cos_fast(double x) { double s, c; plant_sincos_fast(x, &s, &c); return c; }
+#define PLANT_DIV(a, b) plant_div_fast((a), (b))
+#define PLANT_SQRT plant_sqrt_fast
 #define PLANT_FABS fabs
-#define PLANT_SIN sin
-#define PLANT_COS cos
-#define PLANT_SINCOS sincos
+#define PLANT_SIN plant_sin_fast
+#define PLANT_COS plant_cos_fast
+#define PLANT_SINCOS plant_sincos_fast
 #define PLANT_TAN tan
 #define PLANT_EXP exp
 #define PLANT_LOG10 log10

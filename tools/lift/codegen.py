@@ -141,6 +141,35 @@ class Emitter:
         cnt = {}
         partner = {(n.op, n.args[0].id): n.id for n in S.G.nodes if n.id in live and n.op in ('sin', 'cos')}
         done_pair = set()
+        # guards: expensive node -> (cond node id, side) when every use funnels into selects on one condition
+        users = {}
+        outs = {o.id for o in outputs if S.is_sym(o)}
+        for n in S.G.nodes:
+            if n.id in live:
+                for x in n.args:
+                    if S.is_sym(x):
+                        users.setdefault(x.id, []).append(n)
+        guards = {}
+        for n in S.G.nodes:
+            if n.id in live and n.op in ('exp', 'pow') and self.fast:
+                conds, frontier, seen, ok = set(), [n], set(), True
+                while frontier and ok:
+                    m = frontier.pop()
+                    if m.id in seen:
+                        continue
+                    seen.add(m.id)
+                    if m.id in outs:
+                        ok = False
+                    for u in users.get(m.id, []):
+                        if u.op == 'select' and m is not u.args[0]:
+                            if u.args[0].op not in ('cmp', 'cmpmask'):
+                                ok = False
+                            conds.add((u.args[0].id, 1 if m is u.args[1] else 2))
+                        elif u.op in ('add', 'sub', 'mul', 'div', 'neg'):
+                            frontier.append(u)
+                        else:
+                            ok = False
+                guards[n.id] = next(iter(conds)) if ok and len(conds) == 1 else None
         for n in S.G.nodes:
             if n.id not in live or n.op == 'const':
                 continue
@@ -155,6 +184,8 @@ class Emitter:
                 L.append('const %s %s = U[%d];' % (R, v, a[0]))
             elif op == 'div' and self.fast and a[1].op == 'const' and S.fval(a[1].args[0]) != 0.0:
                 L.append('const %s %s = %s * %s;' % (R, v, r(a[0]), self.lit(1.0 / S.fval(a[1].args[0]))))   # x / c -> x * (1/c)
+            elif op == 'div' and self.fast:
+                L.append('const %s %s = PLANT_DIV(%s, %s);' % (R, v, r(a[0]), r(a[1])))
             elif op in ('add', 'sub', 'mul', 'div'):
                 sym = {'add': '+', 'sub': '-', 'mul': '*', 'div': '/'}[op]
                 L.append('const %s %s = %s %s %s;' % (R, v, r(a[0]), sym, r(a[1])))
@@ -183,6 +214,14 @@ class Emitter:
                     sn, cn = (v, 'v%d' % other) if op == 'sin' else ('v%d' % other, v)
                     L.append('%s %s, %s; PLANT_SINCOS(%s, &%s, &%s);' % (R, sn, cn, r(a[0]), sn, cn))
                     done_pair.add((op, a[0].id)); done_pair.add((('cos' if op == 'sin' else 'sin'), a[0].id))
+            elif op == 'tan' and self.fast and ('sin', a[0].id) in partner and ('cos', a[0].id) in partner:
+                L.append('const %s %s = PLANT_DIV(v%d, v%d);' % (R, v, partner['sin', a[0].id], partner['cos', a[0].id]))
+            elif op in ('exp', 'pow') and self.fast and guards.get(n.id) is not None:
+                # only one side of a select consumes this value: evaluate it under that condition (both sides of the
+                # ISA-atmosphere switch are otherwise computed at every stage)
+                cid, side = guards[n.id]
+                call = 'PLANT_EXP(%s)' % r(a[0]) if op == 'exp' else 'PLANT_POW(%s, %s)' % (r(a[0]), r(a[1]))
+                L.append('%s %s = 0.0; if (%sv%d) %s = %s;' % (R, v, '' if side == 1 else '!', cid, v, call))
             elif op in ('sin', 'cos', 'tan', 'exp', 'log10'):
                 L.append('const %s %s = PLANT_%s(%s);' % (R, v, op.upper(), r(a[0])))
             elif op == 'pow':
