@@ -61,7 +61,7 @@ int64_t serl_actor_num_params(const serl_actor_shape* shape);
  *   d_steps     [pop, n_envs] int32 executed steps
  *   d_fitness   [pop] f64 mean over envs (agent.py:245), may be NULL
  *   d_trace     optional [pop, n_envs, horizon, SERL_TRACE_COLS] f64 per-step record (Episode fields, core/utils.py:12-36):
- *               0-11 state before the step (psi, x_e, y_e = NaN-free only in the full-state build),
+ *               0-11 state before the step (psi, x_e, y_e are integrated only when a trace is requested),
  *               12-14 commanded deflection last_u, 15 reward, 16-18 action fed to the env, 19-21 tracking error
  */
 #define SERL_TRACE_COLS 22

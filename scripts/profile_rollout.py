@@ -11,6 +11,7 @@ ap.add_argument('--envs', type=int, default=128)
 ap.add_argument('--horizon', type=int, default=200)
 ap.add_argument('--iters', type=int, default=3)
 ap.add_argument('--mixed', action='store_true')
+ap.add_argument('--sorted', action='store_true')
 a = ap.parse_args()
 dev = torch.device('cuda:0')
 sh = rollout.actor_shape(72)
@@ -19,6 +20,8 @@ lv, st = refsig.make_ref_params(a.envs)
 modes = ['nominal'] * a.envs
 if a.mixed:
     modes = [['nominal', 'be', 'jr', 'sa', 'se', 'ice', 'cg'][i % 7] for i in range(a.envs)]
+if a.sorted:
+    modes = sorted(modes, key=rollout.mode_code)
 md = torch.tensor([rollout.mode_code(m) for m in modes], dtype=torch.int32, device=dev)
 lv, st = torch.from_numpy(lv).to(dev), torch.from_numpy(st).to(dev)
 r = None

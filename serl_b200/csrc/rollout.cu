@@ -110,6 +110,7 @@ __device__ __forceinline__ double plant_cos_fast(double x) { double s, c; plant_
 #include "gen/plant_rhs_cg_for.h"
 #include "gen/plant_rhs_h2000_v150.h"
 #include "gen/plant_rhs_h10000_v90.h"
+#include "gen/plant_rhs_nav.h"
 
 #define ROLLOUT_THREADS 128
 #define NX 19
@@ -143,7 +144,7 @@ __device__ __forceinline__ const double* plant_ic(int variant)
 // Simulink fixed-step ode5 exactly as inlined in the reference's step(): stage states are
 // y + (f0*hB0 + f1*hB1 + ...) with hB = h*B[s][j], summed left to right (zero coefficients included).
 // Fully unrolled so that every f[j][i] load of a stage is independent and the h*B products fold to constants.
-__device__ void plant_step(int variant, double* X, const double* U, const double* tab)
+__device__ void plant_step(int variant, double* X, const double* U, const double* tab, bool nav = false)
 {
     constexpr double h = 0.01;
     constexpr double B[6][6] = {
@@ -154,9 +155,9 @@ __device__ void plant_step(int variant, double* X, const double* U, const double
         {9017.0 / 3168.0, -355.0 / 33.0, 46732.0 / 5247.0, 49.0 / 176.0, -5103.0 / 18656.0, 0},
         {35.0 / 384.0, 0, 500.0 / 1113.0, 125.0 / 192.0, -2187.0 / 6784.0, 11.0 / 84.0}};
     constexpr int LIVE[14] = {0, 1, 2, 3, 4, 5, 6, 7, 9, 12, 15, 16, 17, 18};
-    double f[6][NX], x[NX];
+    double f[6][NX], x[NX], X0[NX];
 #pragma unroll
-    for (int i = 0; i < NX; ++i) { x[i] = X[i]; }
+    for (int i = 0; i < NX; ++i) { x[i] = X[i]; X0[i] = X[i]; }
 #pragma unroll
     for (int s = 0; s < 6; ++s) {
         plant_rhs(variant, x, U, f[s], tab);
@@ -171,6 +172,39 @@ __device__ void plant_step(int variant, double* X, const double* U, const double
     }
 #pragma unroll
     for (int li = 0; li < 14; ++li) X[LIVE[li]] = x[LIVE[li]];
+    if (nav) {
+        // trace mode: psi, x_e, y_e (rtX 8, 10, 11) with the same stage states; their derivatives depend on the live
+        // states only, so they are integrated after the fact from the stored stage derivatives of the live states.
+        double g[6][3], xs[NX];
+#pragma unroll 1
+        for (int s = 0; s < 6; ++s) {
+            // stage state s = X0 + sum_{j<s} hB[s-1][j] f_j  (live part recomputed from f, nav part from g)
+            for (int i = 0; i < NX; ++i) xs[i] = X0[i];
+            if (s > 0) {
+                for (int li = 0; li < 14; ++li) {
+                    const int i = LIVE[li];
+                    double acc = f[0][i] * (h * B[s - 1][0]);
+                    for (int j = 1; j < s; ++j) acc += f[j][i] * (h * B[s - 1][j]);
+                    xs[i] = X0[i] + acc;
+                }
+                const int NAV[3] = {8, 10, 11};
+                for (int q = 0; q < 3; ++q) {
+                    double acc = g[0][q] * (h * B[s - 1][0]);
+                    for (int j = 1; j < s; ++j) acc += g[j][q] * (h * B[s - 1][j]);
+                    xs[NAV[q]] = X0[NAV[q]] + acc;
+                }
+            }
+            double xd[NX];
+            plant_rhs_nav(xs, U, xd, tab);
+            g[s][0] = xd[8]; g[s][1] = xd[10]; g[s][2] = xd[11];
+        }
+        const int NAV[3] = {8, 10, 11};
+        for (int q = 0; q < 3; ++q) {
+            double acc = g[0][q] * (h * B[5][0]);
+            for (int j = 1; j < 6; ++j) acc += g[j][q] * (h * B[5][j]);
+            X[NAV[q]] = X0[NAV[q]] + acc;
+        }
+    }
 }
 
 __device__ __forceinline__ float act_fn(int act, float x)
@@ -240,7 +274,7 @@ __device__ void env_reset(Env& e, const RolloutArgs& a, int env, float* obs)
     e.theta_trim = e.X[7] * RAD2DEG;
     double U[3] = {0.0, 0.0, 0.0}, cmd[3];
     apply_fault(e.fault, U, cmd);
-    plant_step(e.variant, e.X, cmd, e.tab);
+    plant_step(e.variant, e.X, cmd, e.tab, a.trace != nullptr);
     e.t = 0.0; e.ret = 0.0; e.k = 0; e.done = false;
 }
 
@@ -274,7 +308,7 @@ __device__ void env_step(Env& e, const RolloutArgs& ar, size_t traj, const float
     double xo[12];
 #pragma unroll
     for (int i = 0; i < 12; ++i) xo[i] = e.X[i];
-    plant_step(e.variant, e.X, cmd, e.tab);
+    plant_step(e.variant, e.X, cmd, e.tab, ar.trace != nullptr);
 
     const double t = e.t;
     const double r_th = ref_deg(e.ref_lv, e.ref_st, t, e.theta_trim) * DEG2RAD;
@@ -583,12 +617,12 @@ rollout_kernel_warp(RolloutArgs ar)
     Env e;
     e.tab = tab;
     float obs[7], a[3];
-    const bool valid = env < ar.n_envs;
+    const bool valid = env < ar.n_envs && actor < ar.pop;
     if (valid) env_reset(e, ar, env, obs);
     else { e.done = true; e.k = 0; e.ret = 0.0;
 #pragma unroll
         for (int i = 0; i < 7; ++i) obs[i] = 0.f; }
-    const size_t traj = (size_t)actor * ar.n_envs + (valid ? env : 0);
+    const size_t traj = valid ? (size_t)actor * ar.n_envs + env : 0;
     while (__any_sync(0xffffffffu, !e.done)) {
         actor_forward_warp<H>(w, L, ar.sh.activation, lane, obs, a);
         if (!e.done) env_step(e, ar, traj, a, obs);

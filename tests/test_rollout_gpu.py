@@ -117,6 +117,10 @@ def test_trace_matches_oracle_trajectory():
     live = [0, 1, 2, 3, 4, 5, 6, 7, 9]
     assert np.abs(tx[:, live] - o['states'][:, live]).max() < 1e-4
     assert np.abs(tx[:50, live] - o['states'][:50, live]).max() < 1e-6
+    nav = [8, 10, 11]                       # psi, x_e, y_e: integrated only in trace mode
+    assert np.abs(tx[:, 8] - o['states'][:, 8]).max() < 1e-4
+    assert np.allclose(tx[:, nav], o['states'][:, nav], rtol=1e-6, atol=1e-3)
+    assert abs(tx[-1, 10]) > 1000.0          # ~90 m/s for 20 s
     assert np.abs(r.trace_u[0, 0, :n].cpu().numpy() - o['actions']).max() < 1e-4
     assert np.abs(r.trace_r[0, 0, :n].cpu().numpy() - o['rewards']).max() < 1e-4
 
