@@ -268,8 +268,31 @@ def run_ours(args):
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_value = total_steps * n_e2e / (e2e_ms.item() * 1e-3)
 
+    # ---- one full generation (rollout + SSNE.epoch: K2 select, host RNG planner, K3-K5), informative, rank-local
+    gen_ms = None
+    epoch_timing = None
+    if world == 1 and not args.no_generation:
+        import random
+        from serl_b200 import evo
+        np.random.seed(7); random.seed(7)
+        times = []
+        for _ in range(2):
+            g0 = torch.cuda.Event(enable_timing=True); g1 = torch.cuda.Event(enable_timing=True)
+            g0.record()
+            r = rollout.population_rollout(w, sh, lv, st, md, horizon=HORIZON, out=res)
+            _, plan = evo.epoch_flat(w, r.fitness, (7, 3, HIDDEN, 3))
+            epoch_timing = plan.timing
+            g1.record(); torch.cuda.synchronize()
+            times.append(g0.elapsed_time(g1))
+        gen_ms = float(np.mean(times))
+        launches_note = 'rollout + fitness_mean per step; a generation adds K2 + K3..K5 launches'
+
     if rank == 0:
         peak, how = peaks()
+        traffic = None
+        tpath = os.path.join(ROOT, 'profiles', 'r01_rollout_traffic.json')
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get('dram_bytes_per_launch')
         per_gpu_steps = total_steps / world
         achieved = BYTES_PER_STEP * per_gpu_steps / (kern_ms * 1e-3) / 1e9
         line = {
@@ -284,7 +307,8 @@ def run_ours(args):
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
             'gpu_launches': int(launches),
-            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
+            'generation_ms': gen_ms, 'epoch_breakdown': (epoch_timing if gen_ms is not None else None),
+            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
                          'peak_source': how, 'kernel': 'rollout_kernel', 'kernel_ms': kern_ms,
                          'note': 'BASELINE metric denominator (208 B/env-step state round-trip model); the kernel keeps state on chip and is '
                                  'bound by fp64/fp32 issue, see fp_issue',
@@ -307,6 +331,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--no-generation', action='store_true', help='skip the rollout+epoch generation timing')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

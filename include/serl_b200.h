@@ -103,6 +103,20 @@ int serl_ssne_mutate(float* d_weights, int32_t pop, int32_t P, const int32_t* d_
                      const int32_t* d_op_off, const int32_t* d_op_kind, const float* d_op_z,
                      float mag32, float super32, void* stream);
 
+/* Host planner (no CUDA): the crossover / mutation op generation of SSNE.epoch (mod_neuro_evo.py:516-523 + :61-93,
+ * :537-539 + :329-369) consuming CPython's `random` and NumPy's legacy RandomState streams draw for draw.
+ * py_state: 624 MT19937 words + index (random.getstate()[1]); py_gauss: {has_cached, cached gauss_next};
+ * np_state: 624 words + pos (np.random.get_state()); all three are advanced in place.  table: [n_params,3] =
+ * (offset, rows, cols).  Returns an opaque handle: query sizes {pairs, crossover ops, mutation segments, mutations, 0},
+ * copy the arrays out ([pairs,6], [ops,3], [seg,3], offsets, kinds, fp32 z), destroy. */
+void* serl_plan_create(uint32_t* py_state, double* py_gauss, uint32_t* np_state, const int32_t* table, int32_t n_params,
+                       const int32_t* unselects, int32_t n_unselects, const int32_t* new_elitists, int32_t n_new_elitists,
+                       const int32_t* offsprings, int32_t n_offsprings, const int32_t* mut_order, int32_t n_mut,
+                       double mutation_prob);
+void serl_plan_sizes(void* plan, int64_t* out5);
+void serl_plan_copy(void* plan, int32_t* pairs, int32_t* ops, int32_t* seg, int32_t* m_off, int32_t* m_kind, float* m_z);
+void serl_plan_destroy(void* plan);
+
 /* number of kernels serl_* entry points have launched so far in this process (bench bookkeeping) */
 int64_t serl_launch_count(void);
 

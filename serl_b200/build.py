@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libserl_b200.so')
-SOURCES = ['common.cu', 'rollout.cu', 'evo.cu']
+SOURCES = ['common.cu', 'rollout.cu', 'evo.cu', 'evo_plan.cpp']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xptxas', '-v']
 
@@ -31,7 +31,7 @@ def build(force=False, verbose=False):
     os.makedirs(os.path.join(HERE, 'build'), exist_ok=True)
     log = []
     for src in SOURCES:
-        obj = os.path.join(HERE, 'build', src.replace('.cu', '.o'))
+        obj = os.path.join(HERE, 'build', src.replace('.cu', '.o').replace('.cpp', '.o'))
         cmd = [nvcc] + NVCC_FLAGS + ['-c', os.path.join(CSRC, src), '-o', obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         log.append(r.stderr)

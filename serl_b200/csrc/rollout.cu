@@ -144,20 +144,64 @@ __device__ __forceinline__ const double* plant_ic(int variant)
 // Simulink fixed-step ode5 exactly as inlined in the reference's step(): stage states are
 // y + (f0*hB0 + f1*hB1 + ...) with hB = h*B[s][j], summed left to right (zero coefficients included).
 // Fully unrolled so that every f[j][i] load of a stage is independent and the h*B products fold to constants.
+// The stage derivatives of the 14 live states are the only per-step scratch that does not fit in registers
+// (6 x 14 doubles of local memory per thread).
+#define ODE5_B_INIT { \
+        {1.0 / 5.0, 0, 0, 0, 0, 0}, \
+        {3.0 / 40.0, 9.0 / 40.0, 0, 0, 0, 0}, \
+        {44.0 / 45.0, -56.0 / 15.0, 32.0 / 9.0, 0, 0, 0}, \
+        {19372.0 / 6561.0, -25360.0 / 2187.0, 64448.0 / 6561.0, -212.0 / 729.0, 0, 0}, \
+        {9017.0 / 3168.0, -355.0 / 33.0, 46732.0 / 5247.0, 49.0 / 176.0, -5103.0 / 18656.0, 0}, \
+        {35.0 / 384.0, 0, 500.0 / 1113.0, 125.0 / 192.0, -2187.0 / 6784.0, 11.0 / 84.0}}
+#define ODE5_LIVE_INIT {0, 1, 2, 3, 4, 5, 6, 7, 9, 12, 15, 16, 17, 18}
+static __constant__ double c_ode5_B[6][6] = ODE5_B_INIT;      // dynamically indexed copy (trace path)
+static __constant__ int c_ode5_live[14] = ODE5_LIVE_INIT;
+
+// trace mode only: psi, x_e, y_e (rtX 8, 10, 11).  Their derivatives depend on the live states alone, so they are
+// integrated after the fact with the same stage states, rebuilt from the stored stage derivatives f[6][NX].
+__device__ __noinline__ void plant_step_nav(double* Xnav, const double* X0, const double (*f)[NX], const double* U, const double* tab)
+{
+    const double h = 0.01;
+    const int NAV[3] = {8, 10, 11};
+    double g[6][3], xs[NX], xd[NX];
+#pragma unroll 1
+    for (int s = 0; s < 6; ++s) {
+        for (int i = 0; i < NX; ++i) xs[i] = X0[i];
+        if (s > 0) {
+            for (int li = 0; li < 14; ++li) {
+                const int i = c_ode5_live[li];
+                double acc = f[0][i] * (h * c_ode5_B[s - 1][0]);
+                for (int j = 1; j < s; ++j) acc += f[j][i] * (h * c_ode5_B[s - 1][j]);
+                xs[i] = X0[i] + acc;
+            }
+            for (int q = 0; q < 3; ++q) {
+                double acc = g[0][q] * (h * c_ode5_B[s - 1][0]);
+                for (int j = 1; j < s; ++j) acc += g[j][q] * (h * c_ode5_B[s - 1][j]);
+                xs[NAV[q]] = X0[NAV[q]] + acc;
+            }
+        }
+        plant_rhs_nav(xs, U, xd, tab);
+        g[s][0] = xd[8]; g[s][1] = xd[10]; g[s][2] = xd[11];
+    }
+    for (int q = 0; q < 3; ++q) {
+        double acc = g[0][q] * (h * c_ode5_B[5][0]);
+        for (int j = 1; j < 6; ++j) acc += g[j][q] * (h * c_ode5_B[5][j]);
+        Xnav[q] = X0[NAV[q]] + acc;
+    }
+}
+
+// Stage loop fully unrolled (every f[j][i] load of a stage is independent, h*B folds to constants); the right-hand
+// sides are __noinline__ calls, so x and the stage derivatives f live in local memory (L1/L2-resident scratch: it is
+// the source of the kernel's DRAM write-back traffic, see profiles/).  A rolled loop with the RHS inlined cuts that
+// traffic 20x but runs 22 % slower (measured), so this form is kept.
 __device__ void plant_step(int variant, double* X, const double* U, const double* tab, bool nav = false)
 {
     constexpr double h = 0.01;
-    constexpr double B[6][6] = {
-        {1.0 / 5.0, 0, 0, 0, 0, 0},
-        {3.0 / 40.0, 9.0 / 40.0, 0, 0, 0, 0},
-        {44.0 / 45.0, -56.0 / 15.0, 32.0 / 9.0, 0, 0, 0},
-        {19372.0 / 6561.0, -25360.0 / 2187.0, 64448.0 / 6561.0, -212.0 / 729.0, 0, 0},
-        {9017.0 / 3168.0, -355.0 / 33.0, 46732.0 / 5247.0, 49.0 / 176.0, -5103.0 / 18656.0, 0},
-        {35.0 / 384.0, 0, 500.0 / 1113.0, 125.0 / 192.0, -2187.0 / 6784.0, 11.0 / 84.0}};
-    constexpr int LIVE[14] = {0, 1, 2, 3, 4, 5, 6, 7, 9, 12, 15, 16, 17, 18};
-    double f[6][NX], x[NX], X0[NX];
+    constexpr double B[6][6] = ODE5_B_INIT;
+    constexpr int LIVE[14] = ODE5_LIVE_INIT;
+    double f[6][NX], x[NX];
 #pragma unroll
-    for (int i = 0; i < NX; ++i) { x[i] = X[i]; X0[i] = X[i]; }
+    for (int i = 0; i < NX; ++i) x[i] = X[i];
 #pragma unroll
     for (int s = 0; s < 6; ++s) {
         plant_rhs(variant, x, U, f[s], tab);
@@ -170,41 +214,13 @@ __device__ void plant_step(int variant, double* X, const double* U, const double
             x[i] = X[i] + acc;
         }
     }
+    if (nav) {
+        double xn[3];
+        plant_step_nav(xn, X, f, U, tab);
+        X[8] = xn[0]; X[10] = xn[1]; X[11] = xn[2];
+    }
 #pragma unroll
     for (int li = 0; li < 14; ++li) X[LIVE[li]] = x[LIVE[li]];
-    if (nav) {
-        // trace mode: psi, x_e, y_e (rtX 8, 10, 11) with the same stage states; their derivatives depend on the live
-        // states only, so they are integrated after the fact from the stored stage derivatives of the live states.
-        double g[6][3], xs[NX];
-#pragma unroll 1
-        for (int s = 0; s < 6; ++s) {
-            // stage state s = X0 + sum_{j<s} hB[s-1][j] f_j  (live part recomputed from f, nav part from g)
-            for (int i = 0; i < NX; ++i) xs[i] = X0[i];
-            if (s > 0) {
-                for (int li = 0; li < 14; ++li) {
-                    const int i = LIVE[li];
-                    double acc = f[0][i] * (h * B[s - 1][0]);
-                    for (int j = 1; j < s; ++j) acc += f[j][i] * (h * B[s - 1][j]);
-                    xs[i] = X0[i] + acc;
-                }
-                const int NAV[3] = {8, 10, 11};
-                for (int q = 0; q < 3; ++q) {
-                    double acc = g[0][q] * (h * B[s - 1][0]);
-                    for (int j = 1; j < s; ++j) acc += g[j][q] * (h * B[s - 1][j]);
-                    xs[NAV[q]] = X0[NAV[q]] + acc;
-                }
-            }
-            double xd[NX];
-            plant_rhs_nav(xs, U, xd, tab);
-            g[s][0] = xd[8]; g[s][1] = xd[10]; g[s][2] = xd[11];
-        }
-        const int NAV[3] = {8, 10, 11};
-        for (int q = 0; q < 3; ++q) {
-            double acc = g[0][q] * (h * B[5][0]);
-            for (int j = 1; j < 6; ++j) acc += g[j][q] * (h * B[5][j]);
-            X[NAV[q]] = X0[NAV[q]] + acc;
-        }
-    }
 }
 
 __device__ __forceinline__ float act_fn(int act, float x)

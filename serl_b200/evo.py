@@ -46,10 +46,10 @@ def _waves(items, reads, writes):
 
 class EvoPlan:
     __slots__ = ('clone_waves', 'cross_waves', 'mut_seg', 'mut_off', 'mut_kind', 'mut_z', 'elite', 'new_elitists',
-                 'offsprings', 'unselects', 'n_cross_ops')
+                 'offsprings', 'unselects', 'n_cross_ops', 'timing')
 
 
-def plan_epoch(index_rank, offsprings_raw, table, population_size, num_elitists, mutation_prob, selection=None):
+def plan_epoch(index_rank, offsprings_raw, table, population_size, num_elitists, mutation_prob, selection=None, native=False):
     """Everything of SSNE.epoch after the tournaments, as op lists. `selection` (dict) receives rl-selection bookkeeping."""
     index_rank = [int(x) for x in index_rank]
     elitist_index = index_rank[:num_elitists]
@@ -81,6 +81,11 @@ def plan_epoch(index_rank, offsprings_raw, table, population_size, num_elitists,
     # :516-523 classic crossover
     if len(unselects) % 2 != 0:
         unselects.append(unselects[random.randrange(len(unselects))])
+    plan.elite = new_elitists[0]
+    plan.new_elitists, plan.offsprings, plan.unselects = new_elitists, offsprings, unselects
+    plan.timing = None
+    if native:
+        return _plan_tail_native(plan, table, index_rank[num_elitists:], mutation_prob)
     pairs, ops = [], []
     rnd, rrange, rint = random.random, random.randrange, random.randint
     for i, j in zip(unselects[0::2], unselects[1::2]):
@@ -127,6 +132,41 @@ def plan_epoch(index_rank, offsprings_raw, table, population_size, num_elitists,
     plan.mut_z = np.asarray(m_z, dtype=np.float64).astype(np.float32)       # fl32(z): torch casts the python scalar first
     plan.elite = new_elitists[0]
     plan.new_elitists, plan.offsprings, plan.unselects = new_elitists, offsprings, unselects
+    return plan
+
+
+def _plan_tail_native(plan, table, mut_order, mutation_prob):
+    """the two heavy loops (crossover op generation, mutation op generation) in C (csrc/evo_plan.cpp), continuing the
+    stdlib `random` and legacy `np.random` streams from their current state and handing the advanced state back."""
+    L = _native.lib()
+    ver, st, gnext = random.getstate()
+    py_state = np.asarray(st, dtype=np.uint32).copy()
+    py_gauss = np.array([0.0 if gnext is None else 1.0, 0.0 if gnext is None else gnext], dtype=np.float64)
+    name, keys, pos, has_gauss, cached = np.random.get_state()
+    np_state = np.concatenate([np.asarray(keys, dtype=np.uint32), np.array([pos], dtype=np.uint32)])
+    tab = np.asarray(table, dtype=np.int32).reshape(-1, 3).copy()
+    i32 = lambda a: np.ascontiguousarray(np.asarray(a, dtype=np.int32))
+    uns, ne, offs, mo = i32(plan.unselects), i32(plan.new_elitists), i32(plan.offsprings), i32(mut_order)
+    vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    L.serl_plan_create.restype = ctypes.c_void_p
+    h = L.serl_plan_create(vp(py_state), vp(py_gauss), vp(np_state), vp(tab), tab.shape[0], vp(uns), uns.shape[0],
+                           vp(ne), ne.shape[0], vp(offs), offs.shape[0], vp(mo), mo.shape[0], ctypes.c_double(mutation_prob))
+    h = ctypes.c_void_p(h)
+    sizes = np.zeros(5, dtype=np.int64)
+    L.serl_plan_sizes(h, vp(sizes))
+    n_pairs, n_ops, n_seg, n_mut = (int(x) for x in sizes[:4])
+    pairs = np.zeros((n_pairs, 6), np.int32); ops = np.zeros((max(n_ops, 1), 3), np.int32)
+    seg = np.zeros((n_seg, 3), np.int32); m_off = np.zeros(n_mut, np.int32); m_kind = np.zeros(n_mut, np.int32)
+    m_z = np.zeros(n_mut, np.float32)
+    L.serl_plan_copy(h, vp(pairs), vp(ops), vp(seg), vp(m_off), vp(m_kind), vp(m_z))
+    L.serl_plan_destroy(h)
+    random.setstate((ver, tuple(int(x) for x in py_state), (py_gauss[1] if py_gauss[0] else None)))
+    np.random.set_state((name, np_state[:624], int(np_state[624]), has_gauss, cached))
+    plan.n_cross_ops = n_ops
+    ops = ops[:n_ops]
+    plan.cross_waves = [(np.asarray(w, dtype=np.int32).reshape(-1, 6), ops)
+                        for w in _waves([tuple(r) for r in pairs.tolist()], lambda p: (p[2], p[3]), lambda p: (p[0], p[1]))]
+    plan.mut_seg, plan.mut_off, plan.mut_kind, plan.mut_z = seg, m_off, m_kind, m_z
     return plan
 
 
@@ -190,8 +230,15 @@ def epoch_flat(weights, fitness, shape, elite_fraction=0.2, mutation_prob=0.9, m
     if not torch.is_tensor(fitness):
         fitness = torch.as_tensor(np.asarray(fitness, dtype=np.float64))
     fitness = fitness.to(device=weights.device, dtype=torch.float64).contiguous()
+    import time
     num_elitists = max(int(elite_fraction * pop), 1)
+    t0 = time.perf_counter()
     index_rank, offs_raw = select_device(fitness, num_elitists)
-    plan = plan_epoch(index_rank, offs_raw, table, pop, num_elitists, mutation_prob, selection)
+    t1 = time.perf_counter()
+    plan = plan_epoch(index_rank, offs_raw, table, pop, num_elitists, mutation_prob, selection, native=True)
+    t2 = time.perf_counter()
     apply_plan(weights, plan, mutation_mag)
+    t3 = time.perf_counter()
+    plan.timing = {'select_ms': 1e3 * (t1 - t0), 'plan_ms': 1e3 * (t2 - t1), 'apply_ms': 1e3 * (t3 - t2),
+                   'mutations': int(plan.mut_off.shape[0]), 'crossover_copies': int(plan.n_cross_ops)}
     return plan.elite, plan

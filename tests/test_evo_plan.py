@@ -48,8 +48,9 @@ def host_select(fit, num_elitists):
     return rank, rank[draws.min(1)]
 
 
+@pytest.mark.parametrize('native', [False, True])
 @pytest.mark.parametrize('case', CASES)
-def test_plan_reproduces_reference_epoch(case):
+def test_plan_reproduces_reference_epoch(case, native):
     before, fit, after = KAT[case + '_before'], KAT[case + '_fitness'], KAT[case + '_after']
     seed = int(KAT[case + '_seed'])
     shape = tuple(int(x) for x in KAT[case + '_shape'])
@@ -60,7 +61,7 @@ def test_plan_reproduces_reference_epoch(case):
     np.random.seed(seed + 1)
     random.seed(seed + 2)
     rank, offs = host_select(fit, ne)
-    plan = evo.plan_epoch(rank, offs, table, pop, ne, 0.9)
+    plan = evo.plan_epoch(rank, offs, table, pop, ne, 0.9, native=native)
     W = before.copy()
     interpret(W, plan, 0.0247682869654)
     assert plan.elite == int(KAT[case + '_elite'])
@@ -93,3 +94,27 @@ def test_plan_matches_oracle_with_ties_and_odd_sizes(seed):
     interpret(W, plan, 0.0247682869654)
     assert plan.elite == elite_o
     assert np.array_equal(W.view(np.uint32), Wo.view(np.uint32))
+
+
+@pytest.mark.parametrize('pop,seed', [(512, 1), (33, 2), (6, 3)])
+def test_native_planner_equals_python_planner_and_leaves_identical_rng_states(pop, seed):
+    """csrc/evo_plan.cpp re-implements CPython's random (MT19937, _randbelow, gauss cache) and NumPy's legacy uniform."""
+    table, P = evo.param_table(7, 3, 72, 3)
+    ne = max(int(0.2 * pop), 1)
+    out = []
+    for native in (False, True):
+        np.random.seed(seed); random.seed(seed)
+        random.gauss(0, 1)                       # leave a cached second variate in the stream
+        fit = np.random.uniform(-3000, -50, pop)
+        rank, offs = host_select(fit, ne)
+        plan = evo.plan_epoch(rank, offs, table, pop, ne, 0.9, native=native)
+        out.append((plan, random.getstate(), np.random.get_state(), random.random(), random.gauss(0, 1), np.random.rand()))
+    a, b = out[0][0], out[1][0]
+    for x, y in ((a.mut_seg, b.mut_seg), (a.mut_off, b.mut_off), (a.mut_kind, b.mut_kind), (a.mut_z, b.mut_z)):
+        assert np.array_equal(x, y)
+    assert len(a.cross_waves) == len(b.cross_waves)
+    for (d1, o1), (d2, o2) in zip(a.cross_waves, b.cross_waves):
+        assert np.array_equal(d1, d2) and np.array_equal(o1, o2)
+    assert out[0][1] == out[1][1]
+    assert np.array_equal(out[0][2][1], out[1][2][1]) and out[0][2][2:] == out[1][2][2:]
+    assert out[0][3:] == out[1][3:]
