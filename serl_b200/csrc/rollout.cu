@@ -30,7 +30,6 @@ typedef double real;
 // right-hand sides address it through the `plant_tab` pointer they are handed.
 #define PLANT_TAB(name) (plant_tab + PT_OFF_##name)
 #define PLANT_XARGS , const double* __restrict__ plant_tab
-#define PLANT_IC(v) static __device__ const double plant_ic_##v[19]
 // ---- fast fp64 math for the device plant (<= ~1 ulp; the oracle keeps the reference's exact operations) -------
 // division: 20-bit hardware reciprocal seed + two Newton steps + one residual correction (9 instructions instead of ~33)
 __device__ __forceinline__ double plant_div_fast(double a, double b)
@@ -104,12 +103,13 @@ __device__ __forceinline__ double plant_cos_fast(double x) { double s, c; plant_
 #define PLANT_CONSTS(n) static __constant__ double plant_k[n]
 #define PLANT_K(i) plant_k[i]
 #include "gen/plant_consts.h"
-#include "gen/plant_rhs_h2000_v90.h"
-#include "gen/plant_rhs_ice.h"
-#include "gen/plant_rhs_cg.h"
-#include "gen/plant_rhs_cg_for.h"
-#include "gen/plant_rhs_h2000_v150.h"
-#include "gen/plant_rhs_h10000_v90.h"
+#define PLANT_IC(v) static __device__ const double plant_ic_unused_##v[19]
+#define PLANT_IC_TABLE static __device__ const double plant_ic_table[SERL_PLANT_COUNT][19]
+#define PLANT_PV_TABLE static __device__ const double plant_pv[SERL_PLANT_COUNT][PLANT_NPV]
+#define PLANT_PV(k) plant_pvrow[k]
+#include "gen/plant_ic.h"
+#include "gen/plant_rhs_common.h"     // h2000_v90, cg, cg_for, h2000_v150, h10000_v90: one function + parameter rows
+#include "gen/plant_rhs_ice.h"        // structurally different build
 #include "gen/plant_rhs_nav.h"
 
 #define ROLLOUT_THREADS 128
@@ -119,33 +119,14 @@ __device__ __forceinline__ double plant_cos_fast(double x) { double s, c; plant_
 // (psi, x_e, y_e never feed back and are integrated only for traces; Parameter_CSTATE(_g) are folded constants).
 __device__ __forceinline__ void plant_rhs(int variant, const double* X, const double* U, double* xdot, const double* tab)
 {
-    switch (variant) {
-    case SERL_PLANT_ICE: plant_rhs_ice(X, U, xdot, tab); break;
-    case SERL_PLANT_CG: plant_rhs_cg(X, U, xdot, tab); break;
-    case SERL_PLANT_CG_FOR: plant_rhs_cg_for(X, U, xdot, tab); break;
-    case SERL_PLANT_H2000_V150: plant_rhs_h2000_v150(X, U, xdot, tab); break;
-    case SERL_PLANT_H10000_V90: plant_rhs_h10000_v90(X, U, xdot, tab); break;
-    default: plant_rhs_h2000_v90(X, U, xdot, tab); break;
-    }
+    if (variant == SERL_PLANT_ICE) plant_rhs_ice(X, U, xdot, tab);
+    else plant_rhs_common(X, U, xdot, tab, plant_pv[variant]);
 }
 
-__device__ __forceinline__ const double* plant_ic(int variant)
-{
-    switch (variant) {
-    case SERL_PLANT_ICE: return plant_ic_ice;
-    case SERL_PLANT_CG: return plant_ic_cg;
-    case SERL_PLANT_CG_FOR: return plant_ic_cg_for;
-    case SERL_PLANT_H2000_V150: return plant_ic_h2000_v150;
-    case SERL_PLANT_H10000_V90: return plant_ic_h10000_v90;
-    default: return plant_ic_h2000_v90;
-    }
-}
+__device__ __forceinline__ const double* plant_ic(int variant) { return plant_ic_table[variant]; }
 
 // Simulink fixed-step ode5 exactly as inlined in the reference's step(): stage states are
 // y + (f0*hB0 + f1*hB1 + ...) with hB = h*B[s][j], summed left to right (zero coefficients included).
-// Fully unrolled so that every f[j][i] load of a stage is independent and the h*B products fold to constants.
-// The stage derivatives of the 14 live states are the only per-step scratch that does not fit in registers
-// (6 x 14 doubles of local memory per thread).
 #define ODE5_B_INIT { \
         {1.0 / 5.0, 0, 0, 0, 0, 0}, \
         {3.0 / 40.0, 9.0 / 40.0, 0, 0, 0, 0}, \

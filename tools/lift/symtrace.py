@@ -867,7 +867,8 @@ class Tracer:
                     st.x[i][k] = a
                 else:
                     st.x[i][k] = select(c, a, b)
-        keys = set(s1.mem.d) | set(s2.mem.d)
+        # deterministic order, relative to the image / stack bases (absolute addresses change from load to load)
+        keys = sorted(set(s1.mem.d) | set(s2.mem.d), key=lambda a: (a - self.img.base) & M64)
         for a in keys:
             v1 = s1.rd64(a) if s1.mem.get(a) is not POISON else POISON
             v2 = s2.rd64(a) if s2.mem.get(a) is not POISON else POISON
