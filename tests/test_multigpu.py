@@ -1,0 +1,48 @@
+"""the N-GPU sharded generation must equal the 1-GPU generation bit for bit (fitness after the
+all-gather, selection, post-epoch genomes).  Needs >= 2 GPUs; skipped on a single-GPU box."""
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _generation(rank, world, port, out):
+    import torch.distributed as dist
+    from serl_b200 import engine, evo, refsig, rollout
+    torch.cuda.set_device(rank)
+    dev = torch.device('cuda', rank)
+    if world > 1:
+        dist.init_process_group('nccl', init_method='tcp://127.0.0.1:%d' % port, rank=rank, world_size=world, device_id=dev)
+    w = np.load(os.path.join(ROOT, 'tests', 'golden', 'actors.npz'))['serl50_pop8_h32_tanh']
+    genomes = torch.as_tensor(np.tile(w, (3, 1))[:21].copy(), device=dev)          # 21 actors: uneven shards
+    genomes += 1e-3 * torch.arange(21, device=dev, dtype=torch.float32)[:, None] / 21
+    lv, st = refsig.make_ref_params(5, seed_base=2024)
+    md = torch.tensor([rollout.mode_code(m) for m in ('nominal', 'be', 'ice', 'cg', 'sa')], dtype=torch.int32, device=dev)
+    sh = rollout.actor_shape(32)
+    fit, r, (lo, hi) = engine.evaluate_population(genomes, sh, torch.as_tensor(lv, device=dev), torch.as_tensor(st, device=dev), md, horizon=500)
+    np.random.seed(5); random.seed(5)
+    elite, plan = evo.epoch_flat(genomes, fit, (7, 3, 32, 3))
+    out[(world, rank)] = (fit.cpu().numpy(), genomes.cpu().numpy(), elite, (lo, hi))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
+def test_two_gpu_generation_equals_single_gpu_bitwise():
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_generation, args=(1, 0, out), nprocs=1, join=True)
+    mp.spawn(_generation, args=(2, 29600 + os.getpid() % 2000, out), nprocs=2, join=True)
+    f1, g1, e1, _ = out[(1, 0)]
+    for r in range(2):
+        f2, g2, e2, (lo, hi) = out[(2, r)]
+        assert hi - lo in (10, 11)
+        assert np.array_equal(f1, f2)                                    # fitness after the all-gather
+        assert e1 == e2
+        assert np.array_equal(g1.view(np.uint32), g2.view(np.uint32))    # post-epoch genomes on every rank
