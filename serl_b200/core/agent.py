@@ -182,8 +182,11 @@ class Agent:
         lv = torch.as_tensor(np.stack([d[0] for d in draws]), device=self.device)
         st = torch.as_tensor(np.stack([d[1] for d in draws]), device=self.device)
         md = torch.full((n_envs,), self.env.mode_code, dtype=torch.int32, device=self.device)
-        fitness, r, (lo, hi) = engine.evaluate_population(self.pop.genomes, self.shape, lv, st, md)
+        want_sm = bool(getattr(self.args, 'population_smoothness', True))
+        fitness, r, (lo, hi) = engine.evaluate_population(self.pop.genomes, self.shape, lv, st, md, actions=want_sm,
+                                                          smooth_fitness=bool(self.args.smooth_fitness))
         steps = r.steps.cpu().numpy() if r is not None else np.zeros((0, n_envs), dtype=np.int32)
+        self._last_smoothness = r.smoothness.cpu().numpy() if (r is not None and getattr(r, 'smoothness', None) is not None) else None
         lengths = [self._final_time(int(s)) for s in steps.reshape(-1)[:256]]     # statistic only; bounded host work
         if self.store_population_transitions and hi > lo:
             # transitions of the last evaluation of every actor (agent.py:236-238), from a traced re-flight of that env
@@ -208,7 +211,10 @@ class Agent:
         pop_fitness = None
         if len(self.pop):
             pop_fitness, lengths, dev_fitness = self.evaluate_population()
-            sm, sm_sd = float('nan'), float('nan')      # per-episode action smoothness of the population: SURVEY.md 8(f) N1
+            if self._last_smoothness is not None:      # K6: per-episode action smoothness on the device (agent.py:242-243)
+                sm, sm_sd = float(np.mean(self._last_smoothness)), float(np.std(self._last_smoothness))
+            else:
+                sm, sm_sd = float('nan'), float('nan')
             ep_len_avg, ep_len_sd = np.mean(lengths), np.std(lengths)
             best_train_fitness = np.max(pop_fitness)
             worst_train_fitness = np.min(pop_fitness)

@@ -230,6 +230,7 @@ struct RolloutArgs {
     const double* ref_levels; const double* ref_starts; const int* env_mode; int n_envs; int horizon;
     const float* action_noise;      // optional [pop, n_envs, horizon, 3]: clipped exploration noise (agent.py:90-93)
     double* returns; int* steps; double* trace;   // trace optional [pop, n_envs, horizon, SERL_TRACE_COLS]
+    double* actions;                // optional [pop, n_envs, horizon, 3]: commanded deflection last_u (smoothness metric)
     int pop;
 };
 
@@ -318,6 +319,10 @@ __device__ void env_step(Env& e, const RolloutArgs& ar, size_t traj, const float
     const bool done = (t >= 20.0) || (fabs(xo[7]) > max_theta) || (fabs(xo[6]) > max_phi) || (xo[9] < 50.0);
     if (done) reward += (-1.0 / 0.01) * (20.0 - t) * 2.0;      // check_bounds penalty (:391-399)
     e.ret += reward;
+    if (ar.actions) {
+        double* au = ar.actions + (traj * ar.horizon + e.k) * 3;
+        au[0] = U[0]; au[1] = U[1]; au[2] = U[2];
+    }
     if (ar.trace) {
         double* tr = ar.trace + (traj * ar.horizon + e.k) * SERL_TRACE_COLS;
 #pragma unroll
@@ -680,6 +685,74 @@ extern "C" int serl_plant_step(double* d_X, const double* d_cmd, const int32_t* 
     return e == cudaSuccess ? SERL_OK : serl_fail_cuda(e, "plant_step_kernel");
 }
 
+// ---- K6: action-smoothness metric (base/core/utils.py:82-120) --------------------------------------------
+// One CTA per trajectory: direct DFT of the three actuator signals over the executed steps N (N = 2001 is 3*23*29,
+// no radix-2 structure; 12 M fp32 MACs per trajectory), frequency-weighted power summed in double:
+//   S = sum_i sum_{k=1}^{N/2-1} f_k |Y_i[k]|^2 dt * 2/N,  f = linspace(dt, 1/(2dt), N/2-1),  result = -sqrt(S)*100*(80/(N dt)).
+__global__ void __launch_bounds__(256)
+smoothness_kernel(const double* __restrict__ actions, const int* __restrict__ steps, int horizon, double dt, double* __restrict__ out)
+{
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    const int traj = blockIdx.x;
+    const int N = steps[traj];
+    const int M = N / 2 - 1;
+    if (M <= 0) { if (threadIdx.x == 0) out[traj] = -0.0; return; }
+    float2* tw = reinterpret_cast<float2*>(sm_raw);            // [N] (cos, sin)(2 pi j / N)
+    float* y0 = reinterpret_cast<float*>(tw + horizon);       // [3][N]
+    float* y1 = y0 + horizon;
+    float* y2 = y1 + horizon;
+    const double* a = actions + (size_t)traj * horizon * 3;
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+        float sv, cv;
+        sincospif(2.0f * (float)n / (float)N, &sv, &cv);
+        tw[n] = make_float2(cv, sv);
+        y0[n] = (float)a[3 * n]; y1[n] = (float)a[3 * n + 1]; y2[n] = (float)a[3 * n + 2];
+    }
+    __syncthreads();
+    const double fstep = M > 1 ? (1.0 / (2.0 * dt) - dt) / (double)(M - 1) : 0.0;
+    double acc = 0.0;
+    for (int k = 1 + threadIdx.x; k <= M; k += blockDim.x) {
+        float r0 = 0.f, i0 = 0.f, r1 = 0.f, i1 = 0.f, r2 = 0.f, i2 = 0.f;
+        int idx = 0;
+        for (int n = 0; n < N; ++n) {
+            const float2 w = tw[idx];
+            const float v0 = y0[n], v1 = y1[n], v2 = y2[n];
+            r0 = fmaf(v0, w.x, r0); i0 = fmaf(v0, w.y, i0);
+            r1 = fmaf(v1, w.x, r1); i1 = fmaf(v1, w.y, i1);
+            r2 = fmaf(v2, w.x, r2); i2 = fmaf(v2, w.y, i2);
+            idx += k;
+            if (idx >= N) idx -= N;
+        }
+        const double p = (double)r0 * r0 + (double)i0 * i0 + (double)r1 * r1 + (double)i1 * i1 + (double)r2 * r2 + (double)i2 * i2;
+        acc += (dt + (double)(k - 1) * fstep) * p;
+    }
+    __shared__ double red[256];
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const double S = red[0] * dt * 2.0 / (double)N;
+        out[traj] = -(sqrt(S) * 100.0 * (80.0 / ((double)N * dt)));
+    }
+}
+
+extern "C" int serl_smoothness(const double* d_actions, const int32_t* d_steps, int32_t n_traj, int32_t horizon, double dt,
+                               double* d_out, void* stream)
+{
+    if (!d_actions || !d_steps || !d_out || n_traj <= 0 || horizon <= 0) return serl_fail(SERL_ERR_ARG, "serl_smoothness: bad argument");
+    const size_t smem = (size_t)horizon * (8 + 12);
+    if (smem > 200 * 1024) return serl_fail(SERL_ERR_UNSUPPORTED, "serl_smoothness: horizon too long for the shared-memory DFT");
+    cudaError_t e = cudaFuncSetAttribute(smoothness_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return serl_fail_cuda(e, "cudaFuncSetAttribute(smoothness)");
+    smoothness_kernel<<<n_traj, 256, smem, (cudaStream_t)stream>>>(d_actions, d_steps, horizon, dt, d_out);
+    serl_count_launch();
+    e = cudaGetLastError();
+    return e == cudaSuccess ? SERL_OK : serl_fail_cuda(e, "smoothness_kernel");
+}
+
 extern "C" int64_t serl_actor_num_params(const serl_actor_shape* s)
 {
     if (!s) return -1;
@@ -704,7 +777,7 @@ static cudaError_t launch_warp(const RolloutArgs& ar, cudaStream_t s)
 extern "C" int serl_rollout(const float* d_weights, int32_t pop, const serl_actor_shape* shape,
                             const double* d_ref_levels, const double* d_ref_starts, const int32_t* d_env_mode,
                             int32_t n_envs, int32_t horizon, const float* d_action_noise,
-                            double* d_returns, int32_t* d_steps, double* d_fitness, double* d_trace, void* stream)
+                            double* d_returns, int32_t* d_steps, double* d_fitness, double* d_trace, double* d_actions, void* stream)
 {
     if (!d_weights || !shape || !d_ref_levels || !d_ref_starts || !d_env_mode || !d_returns || !d_steps)
         return serl_fail(SERL_ERR_ARG, "serl_rollout: null pointer argument");
@@ -722,7 +795,7 @@ extern "C" int serl_rollout(const float* d_weights, int32_t pop, const serl_acto
     RolloutArgs ar;
     ar.weights = d_weights; ar.P = (int)serl_actor_num_params(shape); ar.sh = *shape;
     ar.ref_levels = d_ref_levels; ar.ref_starts = d_ref_starts; ar.env_mode = d_env_mode; ar.n_envs = n_envs; ar.horizon = horizon;
-    ar.action_noise = d_action_noise; ar.returns = d_returns; ar.steps = d_steps; ar.trace = d_trace; ar.pop = pop;
+    ar.action_noise = d_action_noise; ar.returns = d_returns; ar.steps = d_steps; ar.trace = d_trace; ar.actions = d_actions; ar.pop = pop;
     const int P4 = (ar.P + 3) & ~3;
     const int H = shape->hidden;
     dim3 grid((n_envs + ROLLOUT_THREADS - 1) / ROLLOUT_THREADS, pop);

@@ -42,14 +42,25 @@ def gather_fitness(local, pop, world, rank, group=None):
     return torch.cat(parts)
 
 
-def evaluate_population(genomes, shape, ref_levels, ref_starts, env_mode, horizon=rollout.HORIZON, group=None):
-    """fitness[pop] (f64, on device, identical on every rank), executed env-steps of this rank, local RolloutResult."""
+def evaluate_population(genomes, shape, ref_levels, ref_starts, env_mode, horizon=rollout.HORIZON, group=None,
+                        actions=False, smooth_fitness=False):
+    """fitness[pop] (f64, on device, identical on every rank), local RolloutResult, (lo, hi) of this rank's actor block.
+    actions=True also records the commanded deflections and computes the per-trajectory smoothness (K6) as
+    result.smoothness [pop_local, n_envs]; smooth_fitness adds it to every episode's return before the mean
+    (base/core/agent.py:128-134)."""
     world, rank = world_info()
     pop = genomes.shape[0]
     lo, hi = shard_bounds(pop, world, rank)
     if hi > lo:
-        r = rollout.population_rollout(genomes[lo:hi], shape, ref_levels, ref_starts, env_mode, horizon=horizon)
+        r = rollout.population_rollout(genomes[lo:hi], shape, ref_levels, ref_starts, env_mode, horizon=horizon,
+                                       actions=actions or smooth_fitness)
         local = r.fitness
+        r.smoothness = None
+        if actions or smooth_fitness:
+            r.smoothness = rollout.smoothness(r.actions, r.steps)
+            r.actions = None                     # 48 KB per trajectory: free it as soon as the metric exists
+            if smooth_fitness:
+                local = (r.returns + r.smoothness).mean(dim=1)
     else:
         r = None
         local = torch.zeros(0, dtype=torch.float64, device=genomes.device)

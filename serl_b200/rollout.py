@@ -39,7 +39,7 @@ def _ptr(t):
 
 
 class RolloutResult:
-    __slots__ = ('returns', 'steps', 'fitness', 'trace')
+    __slots__ = ('returns', 'steps', 'fitness', 'trace', 'actions', 'smoothness')
 
     # views into the trace record (include/serl_b200.h: SERL_TRACE_COLS)
     trace_x = property(lambda s: s.trace[..., 0:12])
@@ -52,7 +52,8 @@ class RolloutResult:
 TRACE_COLS = 22
 
 
-def population_rollout(weights, shape, ref_levels, ref_starts, env_mode, horizon=HORIZON, trace=False, out=None, action_noise=None):
+def population_rollout(weights, shape, ref_levels, ref_starts, env_mode, horizon=HORIZON, trace=False, out=None, action_noise=None,
+                       actions=False):
     """weights [pop,P] fp32 cuda; ref_levels/ref_starts [n_envs,2,6] f64 cuda; env_mode [n_envs] int32 cuda."""
     if not weights.is_cuda:
         raise _native.NativeError('population_rollout needs CUDA tensors (no CPU fallback)')
@@ -73,11 +74,26 @@ def population_rollout(weights, shape, ref_levels, ref_starts, env_mode, horizon
         r.steps = torch.empty((pop, n_envs), dtype=torch.int32, device=dev)
         r.fitness = torch.empty((pop,), dtype=torch.float64, device=dev)
         r.trace = None
+        r.actions = torch.empty((pop, n_envs, horizon, 3), dtype=torch.float64, device=dev) if actions else None
         if trace:
             r.trace = torch.full((pop, n_envs, horizon, TRACE_COLS), float('nan'), dtype=torch.float64, device=dev)
     stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
     rc = L.serl_rollout(_ptr(weights), pop, ctypes.byref(shape), _ptr(ref_levels), _ptr(ref_starts), _ptr(env_mode),
                         n_envs, horizon, _ptr(action_noise), _ptr(r.returns), _ptr(r.steps), _ptr(r.fitness),
-                        _ptr(r.trace), stream)
+                        _ptr(r.trace), _ptr(getattr(r, 'actions', None)), stream)
     _native.check(rc, 'serl_rollout')
     return r
+
+
+def smoothness(actions, steps, dt=0.01):
+    """K6: per-trajectory action smoothness (core/utils.py calc_smoothness) of `actions` [..., horizon, 3] f64 (cuda) over the
+    first `steps` [...] executed steps. Returns f64 tensor shaped like `steps`."""
+    L = _native.lib()
+    horizon = actions.shape[-2]
+    n = steps.numel()
+    assert actions.is_cuda and actions.dtype == torch.float64 and actions.is_contiguous() and actions.numel() == n * horizon * 3
+    st = steps.contiguous().to(torch.int32)
+    out = torch.empty(st.shape, dtype=torch.float64, device=actions.device)
+    stream = ctypes.c_void_p(torch.cuda.current_stream(actions.device).cuda_stream)
+    _native.check(L.serl_smoothness(_ptr(actions), _ptr(st), n, horizon, dt, _ptr(out), stream), 'serl_smoothness')
+    return out

@@ -126,3 +126,26 @@ def test_agent_train_generations_and_checkpoint_format():
     assert list(pop_dict['actor_0'])[:2] == ['net.0.weight', 'net.0.bias']
     oracle_actor = OA.from_state_dict(torch.load('/tmp/serl_test/elite_net.pkl', weights_only=False), 'tanh')   # loads into the reference layout
     assert np.array_equal(OA.flatten(oracle_actor), ag.pop.genomes[int(stats['elite_index'])].cpu().numpy())
+
+
+def test_smoothness_kernel_matches_reference_formula():
+    """K6 vs calc_smoothness (base/core/utils.py:82-120) on real action histories, incl. an early-terminated episode."""
+    from serl_b200 import rollout
+    from serl_b200.core.utils import calc_smoothness
+    from oracle import refsig
+    acts = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'actors.npz'))
+    torch.manual_seed(7)
+    w = np.concatenate([acts['serl10_pop_h72_tanh'][:2], np.stack([OA.flatten(OA.Actor(hidden=72)) for _ in range(2)])])
+    lv, st = refsig.make_ref_params(3, seed_base=17)
+    dev = torch.device('cuda:0')
+    md = torch.tensor([rollout.mode_code(m) for m in ('nominal', 'be', 'ice')], dtype=torch.int32, device=dev)
+    r = rollout.population_rollout(torch.as_tensor(w, device=dev), rollout.actor_shape(72), torch.as_tensor(lv, device=dev),
+                                   torch.as_tensor(st, device=dev), md, actions=True)
+    sm = rollout.smoothness(r.actions, r.steps).cpu().numpy()
+    steps = r.steps.cpu().numpy()
+    a = r.actions.cpu().numpy()
+    assert (steps < 2001).any() and (steps == 2001).any()
+    for i in range(4):
+        for e in range(3):
+            ref = calc_smoothness(a[i, e, :steps[i, e]])
+            assert abs(sm[i, e] - ref) <= 2e-5 * abs(ref) + 1e-9, (i, e, sm[i, e], ref)

@@ -81,16 +81,16 @@ def test_capi_argument_errors_are_reported():
     ret = torch.zeros((1, 1), dtype=torch.float64, device=dev)
     stp = torch.zeros((1, 1), dtype=torch.int32, device=dev)
     p = lambda t: ctypes.c_void_p(t.data_ptr())
-    rc = L.serl_rollout(None, 1, ctypes.byref(sh), p(lv), p(lv), p(md), 1, 10, None, p(ret), p(stp), None, None, None)
+    rc = L.serl_rollout(None, 1, ctypes.byref(sh), p(lv), p(lv), p(md), 1, 10, None, p(ret), p(stp), None, None, None, None)
     assert rc == -1 and b'null pointer' in L.serl_last_error()
-    rc = L.serl_rollout(p(w), 0, ctypes.byref(sh), p(lv), p(lv), p(md), 1, 10, None, p(ret), p(stp), None, None, None)
+    rc = L.serl_rollout(p(w), 0, ctypes.byref(sh), p(lv), p(lv), p(md), 1, 10, None, p(ret), p(stp), None, None, None, None)
     assert rc == -1
     bad = rollout.actor_shape(72); bad.state_dim = 9
-    rc = L.serl_rollout(p(w), 1, ctypes.byref(bad), p(lv), p(lv), p(md), 1, 10, None, p(ret), p(stp), None, None, None)
+    rc = L.serl_rollout(p(w), 1, ctypes.byref(bad), p(lv), p(lv), p(md), 1, 10, None, p(ret), p(stp), None, None, None, None)
     assert rc == -1 and b'state_dim' in L.serl_last_error()
     big = rollout.actor_shape(128)
     wb = torch.zeros((1, rollout.num_params(big)), device=dev)
-    rc = L.serl_rollout(p(wb), 1, ctypes.byref(big), p(lv), p(lv), p(md), 1, 10, None, p(ret), p(stp), None, None, None)
+    rc = L.serl_rollout(p(wb), 1, ctypes.byref(big), p(lv), p(lv), p(md), 1, 10, None, p(ret), p(stp), None, None, None, None)
     assert rc == -3          # SERL_ERR_UNSUPPORTED: genome does not fit in shared memory
     with pytest.raises(_native.NativeError):
         _native.check(rc, 'serl_rollout')
