@@ -271,6 +271,7 @@ def run_ours(args):
     # ---- one full generation (rollout + SSNE.epoch: K2 select, host RNG planner, K3-K5), informative, rank-local
     gen_ms = None
     epoch_timing = None
+    smooth_timing = None
     if world == 1 and not args.no_generation:
         import random
         from serl_b200 import evo
@@ -285,6 +286,16 @@ def run_ours(args):
             g1.record(); torch.cuda.synchronize()
             times.append(g0.elapsed_time(g1))
         gen_ms = float(np.mean(times))
+        # the same with the action-smoothness metric of every episode (K6; agent.py:128-134, -smooth_fitness)
+        s0 = torch.cuda.Event(enable_timing=True); s1 = torch.cuda.Event(enable_timing=True); s2 = torch.cuda.Event(enable_timing=True)
+        s0.record()
+        r = rollout.population_rollout(w, sh, lv, st, md, horizon=HORIZON, actions=True)
+        s1.record()
+        sm = rollout.smoothness(r.actions, r.steps)
+        s2.record(); torch.cuda.synchronize()
+        smooth_timing = {'rollout_with_action_history_ms': s0.elapsed_time(s1), 'smoothness_kernel_ms': s1.elapsed_time(s2),
+                         'action_history_bytes': int(r.actions.numel() * 8)}
+        del r, sm
         launches_note = 'rollout + fitness_mean per step; a generation adds K2 + K3..K5 launches'
 
     if rank == 0:
@@ -307,7 +318,7 @@ def run_ours(args):
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
             'gpu_launches': int(launches),
-            'generation_ms': gen_ms, 'epoch_breakdown': (epoch_timing if gen_ms is not None else None),
+            'generation_ms': gen_ms, 'epoch_breakdown': (epoch_timing if gen_ms is not None else None), 'smoothness': smooth_timing,
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
                          'peak_source': how, 'kernel': 'rollout_kernel', 'kernel_ms': kern_ms,
                          'note': 'BASELINE metric denominator (208 B/env-step state round-trip model); the kernel keeps state on chip and is '
