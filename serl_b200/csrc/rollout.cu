@@ -14,7 +14,7 @@
 //   rollout_kernel_warp<H>  warp-autonomous: a warp owns 32 envs of one actor and never synchronises with other
 //                           warps.  The MLP is a register-tiled GEMM inside the warp (lane = 1/4 of the output neurons
 //                           x 4 envs, activations exchanged with warp shuffles, weights broadcast from shared memory);
-//                           plant tables live in shared memory next to the genomes.      (h in {32,64,72,96})
+//                           plant tables live in shared memory next to the genomes.  (h in {32,64,72,96,128})
 //   rollout_kernel_simple   every thread runs the whole MLP for its env (any h that fits); reference / fallback shape.
 #include <cuda_runtime.h>
 #include <math.h>
@@ -571,21 +571,25 @@ __device__ void actor_forward_warp(const float* __restrict__ w, int L, int actfn
     }
 }
 
-template <int H, int APC>
+// TABS: plant tables staged in shared memory (true) or read from global memory through L1 (false: h = 128, whose
+// 207 KB genome leaves no room for them).
+template <int H, int APC, bool TABS>
 __global__ void __launch_bounds__(ROLLOUT_THREADS * APC, 1)
 rollout_kernel_warp(RolloutArgs ar)
 {
     constexpr int S = 7;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* tab = reinterpret_cast<double*>(smem_raw);
-    float* wbase = reinterpret_cast<float*>(tab + PT_TOTAL);
+    double* tab_s = reinterpret_cast<double*>(smem_raw);
+    float* wbase = reinterpret_cast<float*>(tab_s + (TABS ? PT_TOTAL : 0));
+    const double* tab = TABS ? tab_s : plant_tables_blob;
     const int L = ar.sh.num_layers;
     const int P4 = (ar.P + 3) & ~3;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int al = warp >> 2;                               // actor slot of this warp inside the CTA
     const int actor = blockIdx.y * APC + al;
     const int env = blockIdx.x * ROLLOUT_THREADS + (warp & 3) * 32 + lane;
-    for (int i = tid; i < PT_TOTAL; i += ROLLOUT_THREADS * APC) tab[i] = plant_tables_blob[i];
+    if (TABS)
+        for (int i = tid; i < PT_TOTAL; i += ROLLOUT_THREADS * APC) tab_s[i] = plant_tables_blob[i];
     // stage the genomes: parameters() order in HBM (row-major [out][in]) -> transposed [in][out] in smem
     for (int slot = 0; slot < APC; ++slot) {
         const int ga = blockIdx.y * APC + slot;
@@ -762,15 +766,15 @@ extern "C" int64_t serl_actor_num_params(const serl_actor_shape* s)
 
 static int g_force_simple = -1;
 
-template <int H, int APC>
+template <int H, int APC, bool TABS>
 static cudaError_t launch_warp(const RolloutArgs& ar, cudaStream_t s)
 {
     const int P4 = (ar.P + 3) & ~3;
-    const size_t smem = (size_t)PT_TOTAL * 8 + (size_t)APC * P4 * 4;
-    cudaError_t e = cudaFuncSetAttribute(rollout_kernel_warp<H, APC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = (TABS ? (size_t)PT_TOTAL * 8 : 0) + (size_t)APC * P4 * 4;
+    cudaError_t e = cudaFuncSetAttribute(rollout_kernel_warp<H, APC, TABS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid((ar.n_envs + ROLLOUT_THREADS - 1) / ROLLOUT_THREADS, (ar.pop + APC - 1) / APC);
-    rollout_kernel_warp<H, APC><<<grid, ROLLOUT_THREADS * APC, smem, s>>>(ar);
+    rollout_kernel_warp<H, APC, TABS><<<grid, ROLLOUT_THREADS * APC, smem, s>>>(ar);
     return cudaGetLastError();
 }
 
@@ -800,15 +804,17 @@ extern "C" int serl_rollout(const float* d_weights, int32_t pop, const serl_acto
     const int H = shape->hidden;
     dim3 grid((n_envs + ROLLOUT_THREADS - 1) / ROLLOUT_THREADS, pop);
     cudaError_t e;
-    const bool warp_ok = !g_force_simple && (H == 32 || H == 64 || H == 72 || H == 96) &&
-                         (size_t)PT_TOTAL * 8 + (size_t)P4 * 4 <= 227 * 1024;
+    const bool warp_ok = !g_force_simple && (H == 32 || H == 64 || H == 72 || H == 96 || H == 128) && (size_t)P4 * 4 <= 227 * 1024;
     if (warp_ok) {
-        // two actors per CTA (8 autonomous warps) when two genomes + the plant tables fit in shared memory
+        // two actors per CTA (8 autonomous warps) when two genomes + the plant tables fit in shared memory; one actor
+        // with the tables in shared memory when that fits; else (h = 128) one actor and the tables through L1
         const bool two = (size_t)PT_TOTAL * 8 + 2ull * P4 * 4 <= 227 * 1024 && pop > 1;
-        if (H == 32) e = two ? launch_warp<32, 2>(ar, s) : launch_warp<32, 1>(ar, s);
-        else if (H == 64) e = two ? launch_warp<64, 2>(ar, s) : launch_warp<64, 1>(ar, s);
-        else if (H == 72) e = two ? launch_warp<72, 2>(ar, s) : launch_warp<72, 1>(ar, s);
-        else e = two ? launch_warp<96, 2>(ar, s) : launch_warp<96, 1>(ar, s);
+        const bool tabs = (size_t)PT_TOTAL * 8 + (size_t)P4 * 4 <= 227 * 1024;
+        if (H == 32) e = two ? launch_warp<32, 2, true>(ar, s) : launch_warp<32, 1, true>(ar, s);
+        else if (H == 64) e = two ? launch_warp<64, 2, true>(ar, s) : launch_warp<64, 1, true>(ar, s);
+        else if (H == 72) e = two ? launch_warp<72, 2, true>(ar, s) : launch_warp<72, 1, true>(ar, s);
+        else if (H == 96) e = launch_warp<96, 1, true>(ar, s);
+        else e = tabs ? launch_warp<128, 1, true>(ar, s) : launch_warp<128, 1, false>(ar, s);
     } else {
         const size_t smem = (size_t)P4 * 4 + 2ull * H * ROLLOUT_THREADS * 4;
         if (smem > 227 * 1024) return serl_fail(SERL_ERR_UNSUPPORTED, "serl_rollout: genome + activations exceed 227 KB of shared memory");

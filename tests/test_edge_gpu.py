@@ -61,6 +61,20 @@ def test_hidden_64_goes_through_the_warp_kernel():
             assert abs(float(r.returns[a, e]) - o['fitness']) <= 1e-4 * abs(o['fitness'])
 
 
+def test_hidden_128_runs_with_tables_in_global_memory():
+    """h = 128: the 207 KB genome fills shared memory, plant tables are read through L1 (kernel variant TABS=false)."""
+    torch.manual_seed(11)
+    w = np.stack([A.flatten(A.Actor(hidden=128)) for _ in range(2)])
+    lv, st = refsig.make_ref_params(2, seed_base=19)
+    r = run(w, 128, lv, st, ['nominal', 'cg'])
+    env = {m: phlab.CitationEnv(m, 'auto') for m in ('nominal', 'cg')}
+    for a in range(2):
+        for e, m in enumerate(('nominal', 'cg')):
+            o = phlab.run_episode(env[m], A.unflatten(w[a], hidden=128), lv[e], st[e])
+            assert int(r.steps[a, e]) == o['steps']
+            assert abs(float(r.returns[a, e]) - o['fitness']) <= 1e-4 * abs(o['fitness'])
+
+
 def test_repeat_launches_are_bitwise_deterministic():
     w = ACT['serl10_pop_h72_tanh'][:3]
     lv, st = refsig.make_ref_params(5, seed_base=77)
@@ -88,10 +102,10 @@ def test_capi_argument_errors_are_reported():
     bad = rollout.actor_shape(72); bad.state_dim = 9
     rc = L.serl_rollout(p(w), 1, ctypes.byref(bad), p(lv), p(lv), p(md), 1, 10, None, p(ret), p(stp), None, None, None, None)
     assert rc == -1 and b'state_dim' in L.serl_last_error()
-    big = rollout.actor_shape(128)
+    big = rollout.actor_shape(160)
     wb = torch.zeros((1, rollout.num_params(big)), device=dev)
     rc = L.serl_rollout(p(wb), 1, ctypes.byref(big), p(lv), p(lv), p(md), 1, 10, None, p(ret), p(stp), None, None, None, None)
-    assert rc == -3          # SERL_ERR_UNSUPPORTED: genome does not fit in shared memory
+    assert rc == -3          # SERL_ERR_UNSUPPORTED: a h=160 genome (324 KB) does not fit in shared memory
     with pytest.raises(_native.NativeError):
         _native.check(rc, 'serl_rollout')
     assert L.serl_ssne_select(None, 4, None, 0, None, None, None) == -1
