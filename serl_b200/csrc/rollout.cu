@@ -715,20 +715,37 @@ smoothness_kernel(const double* __restrict__ actions, const int* __restrict__ st
     __syncthreads();
     const double fstep = M > 1 ? (1.0 / (2.0 * dt) - dt) / (double)(M - 1) : 0.0;
     double acc = 0.0;
-    for (int k = 1 + threadIdx.x; k <= M; k += blockDim.x) {
-        float r0 = 0.f, i0 = 0.f, r1 = 0.f, i1 = 0.f, r2 = 0.f, i2 = 0.f;
-        int idx = 0;
-        for (int n = 0; n < N; ++n) {
-            const float2 w = tw[idx];
-            const float v0 = y0[n], v1 = y1[n], v2 = y2[n];
-            r0 = fmaf(v0, w.x, r0); i0 = fmaf(v0, w.y, i0);
-            r1 = fmaf(v1, w.x, r1); i1 = fmaf(v1, w.y, i1);
-            r2 = fmaf(v2, w.x, r2); i2 = fmaf(v2, w.y, i2);
-            idx += k;
-            if (idx >= N) idx -= N;
+    // four frequencies per thread and pass: every y[n] broadcast load feeds 8 fmas per signal
+    for (int kb = 1 + 4 * threadIdx.x; kb <= M; kb += 4 * blockDim.x) {
+        float re[4][3], im[4][3];
+        int idx[4], kk[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            kk[q] = (kb + q <= M) ? kb + q : 0;        // k = 0 is a harmless dummy (weight 0 below)
+            idx[q] = 0;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { re[q][c] = 0.f; im[q][c] = 0.f; }
         }
-        const double p = (double)r0 * r0 + (double)i0 * i0 + (double)r1 * r1 + (double)i1 * i1 + (double)r2 * r2 + (double)i2 * i2;
-        acc += (dt + (double)(k - 1) * fstep) * p;
+        for (int n = 0; n < N; ++n) {
+            const float v0 = y0[n], v1 = y1[n], v2 = y2[n];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float2 w = tw[idx[q]];
+                re[q][0] = fmaf(v0, w.x, re[q][0]); im[q][0] = fmaf(v0, w.y, im[q][0]);
+                re[q][1] = fmaf(v1, w.x, re[q][1]); im[q][1] = fmaf(v1, w.y, im[q][1]);
+                re[q][2] = fmaf(v2, w.x, re[q][2]); im[q][2] = fmaf(v2, w.y, im[q][2]);
+                idx[q] += kk[q];
+                if (idx[q] >= N) idx[q] -= N;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (kk[q] == 0) continue;
+            double p = 0.0;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) p += (double)re[q][c] * re[q][c] + (double)im[q][c] * im[q][c];
+            acc += (dt + (double)(kk[q] - 1) * fstep) * p;
+        }
     }
     __shared__ double red[256];
     red[threadIdx.x] = acc;
