@@ -1,24 +1,30 @@
-"""Mirror of the pieces of base/core/mod_utils.py the hot path and its callers use."""
+"""Host-side helpers with the names the reference's callers import from base/core/mod_utils.py
+(activations :14-18, soft/hard target updates :25-34, LayerNorm :39-50, Gaussian exploration noise, is_lnorm_key :130)."""
 import numpy as np
 import torch
-import torch.nn as nn
+from torch import nn
 
-# base/core/mod_utils.py:14-18 ('relu' is LeakyReLU in the reference)
-activations = {'tanh': nn.Tanh(), 'elu': nn.ELU(), 'relu': nn.LeakyReLU()}
+# name -> module; note the reference maps 'relu' to LeakyReLU (mod_utils.py:17)
+activations = dict(tanh=nn.Tanh(), elu=nn.ELU(), relu=nn.LeakyReLU())
 
 
+@torch.no_grad()
 def soft_update(target, source, tau):
-    for target_param, param in zip(target.parameters(), source.parameters()):
-        target_param.data.copy_(target_param.data * (1.0 - tau) + param.data * tau)
+    """Polyak averaging target <- (1 - tau) * target + tau * source."""
+    for t, s in zip(target.parameters(), source.parameters()):
+        t.mul_(1.0 - tau).add_(s, alpha=tau)
 
 
+@torch.no_grad()
 def hard_update(target, source):
-    for target_param, param in zip(target.parameters(), source.parameters()):
-        target_param.data.copy_(param.data)
+    for t, s in zip(target.parameters(), source.parameters()):
+        t.copy_(s)
 
 
 class LayerNorm(nn.Module):
-    """base/core/mod_utils.py:39-50: unbiased std, eps added to the std."""
+    """The reference's own normalisation (not torch.nn.LayerNorm): Bessel-corrected standard deviation over the last
+    axis with eps added to the *standard deviation*, then an affine map (parameters named gamma / beta so that
+    checkpoints keep the keys net.{3,6,9}.{gamma,beta})."""
 
     def __init__(self, features, eps=1e-6):
         super().__init__()
@@ -27,9 +33,9 @@ class LayerNorm(nn.Module):
         self.eps = eps
 
     def forward(self, x):
-        mean = x.mean(-1, keepdim=True)
-        std = x.std(-1, keepdim=True)
-        return self.gamma * (x - mean) / (std + self.eps) + self.beta
+        centred = x - x.mean(dim=-1, keepdim=True)
+        spread = x.std(dim=-1, keepdim=True) + self.eps
+        return self.gamma * centred / spread + self.beta
 
 
 class GaussianNoise:

@@ -1,4 +1,6 @@
-"""Minimal mirror of base/core/replay_memory.py:13-100 (uniform ring buffer of (state, action, next_state, reward, done))."""
+"""Uniform replay ring buffer with the interface the reference's callers use (base/core/replay_memory.py:13-100:
+add / add_content_of / get_latest / sample / reset / len), stored as preallocated numpy arrays instead of a list of
+namedtuples.  Host-side bookkeeping of the RL half; not on the GPU hot path."""
 import random
 from collections import namedtuple
 
@@ -10,40 +12,45 @@ Transition = namedtuple('Transition', ('state', 'action', 'next_state', 'reward'
 
 class ReplayMemory:
     def __init__(self, capacity, device):
-        self.device, self.capacity = device, capacity
-        self.memory, self.position = [], 0
+        self.capacity, self.device = int(capacity), device
+        self._store = None          # dict of field -> [capacity, dim] float32
+        self._count = 0             # transitions ever written
+        self.position = 0
 
     def reset(self):
-        self.memory, self.position = [], 0
-
-    def add(self, *args):
-        if len(self.memory) < self.capacity:
-            self.memory.append(None)
-        reshaped = [np.reshape(np.asarray(a, dtype=np.float32), (1, -1)) for a in args]
-        self.memory[self.position] = Transition(*reshaped)
-        self.position = (self.position + 1) % self.capacity
-
-    def add_content_of(self, other):
-        latest = other.get_latest(self.capacity)
-        for t in latest:
-            self.add(*t)
-
-    def get_latest(self, latest):
-        if self.capacity < latest:
-            latest_trans = self.memory[self.position:].copy() + self.memory[:self.position].copy()
-        elif len(self.memory) < self.capacity:
-            latest_trans = self.memory[-latest:].copy()
-        elif self.position >= latest:
-            latest_trans = self.memory[:self.position][-latest:].copy()
-        else:
-            latest_trans = self.memory[-latest + self.position:].copy() + self.memory[:self.position].copy()
-        return latest_trans
-
-    def sample(self, batch_size):
-        transitions = random.sample(self.memory, batch_size)
-        batch = Transition(*zip(*transitions))
-        f = lambda xs: torch.FloatTensor(np.concatenate(xs)).to(self.device)
-        return f(batch.state), f(batch.action), f(batch.next_state), f(batch.reward), f(batch.done)
+        self._count, self.position = 0, 0
 
     def __len__(self):
-        return len(self.memory)
+        return min(self._count, self.capacity)
+
+    def add(self, state, action, next_state, reward, done):
+        row = [np.asarray(v, dtype=np.float32).reshape(-1) for v in (state, action, next_state, reward, done)]
+        if self._store is None:
+            self._store = {f: np.zeros((self.capacity, r.shape[0]), dtype=np.float32) for f, r in zip(Transition._fields, row)}
+        for f, r in zip(Transition._fields, row):
+            self._store[f][self.position] = r
+        self.position = (self.position + 1) % self.capacity
+        self._count += 1
+
+    def _chronological(self):
+        n = len(self)
+        if self._count <= self.capacity:
+            return np.arange(n)
+        return (np.arange(n) + self.position) % self.capacity
+
+    def get_latest(self, latest):
+        order = self._chronological()[-int(latest):]
+        return [Transition(*(self._store[f][i:i + 1].copy() for f in Transition._fields)) for i in order]
+
+    def add_content_of(self, other):
+        if other._store is None:
+            return
+        for i in other._chronological()[-self.capacity:]:
+            self.add(*(other._store[f][i] for f in Transition._fields))
+
+    def sample(self, batch_size):
+        # same stdlib-`random` consumption as the reference's random.sample(self.memory, batch_size) (:66), so that the
+        # stream position seen by the next SSNE.epoch does not depend on which buffer implementation is used
+        order = self._chronological() if self._count > self.capacity else None
+        pick = np.asarray(random.sample(range(len(self)), batch_size))
+        return tuple(torch.from_numpy(self._store[f][pick]).to(self.device) for f in Transition._fields)

@@ -1,5 +1,5 @@
-"""Mirror of base/core/utils.py: the Episode record returned by Agent.evaluate, the action-smoothness metric, config loading."""
-import os
+"""`Episode` (the record Agent.evaluate returns, base/core/utils.py:12-36), the host version of the action-smoothness
+metric (:82-120; the device version is csrc/rollout.cu smoothness_kernel) and the wandb-config loader (:123-146)."""
 from dataclasses import dataclass
 from pathlib import Path
 from typing import List
@@ -9,7 +9,6 @@ import numpy as np
 
 @dataclass
 class Episode:
-    """base/core/utils.py:12-36"""
     fitness: np.float64
     smoothness: np.float64
     length: np.float64
@@ -19,30 +18,33 @@ class Episode:
     reward_lst: List
 
     def get_history(self) -> np.ndarray:
-        """[refs, actions, states, reward] per step, shape (ep_len, 19) (utils.py:24-36)."""
-        tt = np.linspace(0, self.length, len(self.state_history))
-        ref_values = np.array([[ref(t_i) for t_i in tt] for ref in self.ref_signals]).transpose()
-        reward_lst = np.asarray(self.reward_lst).reshape((len(self.state_history), 1))
-        return np.concatenate((ref_values, self.actions, self.state_history, reward_lst), axis=1)
+        """Time traces [3 references | 3 actuator commands | 12 states | reward], one row per step."""
+        steps = len(self.state_history)
+        t_axis = np.linspace(0, self.length, steps)
+        refs = np.stack([[signal(t) for t in t_axis] for signal in self.ref_signals], axis=1)
+        rewards = np.asarray(self.reward_lst, dtype=np.float64).reshape(steps, 1)
+        return np.hstack([refs, np.asarray(self.actions), np.asarray(self.state_history), rewards])
 
 
 def calc_smoothness(y: np.ndarray, dt: float = 0.01, **kwargs) -> float:
-    """base/core/utils.py:82-120 (host-side; the device version is SURVEY.md 8(f) N1)."""
-    N, A = y.shape[0], y.shape[1]
-    T = N * dt
-    freq = np.linspace(dt, 1 / (2 * dt), N // 2 - 1)
-    Syy = np.zeros((N // 2 - 1, A))
-    for i in range(A):
-        Y = np.fft.fft(y[:, i], N)
-        Syy_disc = Y[1:N // 2] * np.conjugate(Y[1:N // 2])
-        Syy[:, i] = np.abs(Syy_disc) * dt
-    signal_roughness = np.einsum('ij,i -> j', Syy, freq) * 2 / N
-    roughness = np.sqrt(np.sum(signal_roughness, axis=-1)) * 100 * (80 / T)
-    return -roughness
+    """-sqrt(sum over channels and frequencies of f * S_yy(f) * 2/N) * 100 * 80/T with S_yy = |FFT(y)|^2 dt over the
+    bins 1 .. N/2-1 and f = linspace(dt, 1/(2 dt), N/2-1)."""
+    n_samples = y.shape[0]
+    bins = n_samples // 2 - 1
+    if bins <= 0:
+        return -0.0
+    spectrum = np.fft.fft(np.asarray(y, dtype=np.float64), n_samples, axis=0)[1:n_samples // 2]
+    power = np.abs(spectrum * np.conjugate(spectrum)) * dt
+    freq = np.linspace(dt, 1 / (2 * dt), bins)
+    roughness_per_channel = (freq[:, None] * power).sum(axis=0) * 2 / n_samples
+    return -(np.sqrt(roughness_per_channel.sum()) * 100 * (80 / (n_samples * dt)))
 
 
 def load_config(model_path: str, verbose: bool = False) -> dict:
+    """Read `<run>/files/config.yaml` as written by wandb ({key: {value: v, desc: ...}}) into a flat dict."""
     import yaml
-    model_path = model_path / Path('files/')
-    conf_raw = yaml.safe_load(Path(os.path.join(model_path, 'config.yaml')).read_text(encoding='utf-8'))
-    return {k: (v['value'] if isinstance(v, dict) else v) for k, v in conf_raw.items()}
+    raw = yaml.safe_load((Path(model_path) / 'files' / 'config.yaml').read_text(encoding='utf-8'))
+    flat = {key: (entry['value'] if isinstance(entry, dict) else entry) for key, entry in raw.items()}
+    if verbose:
+        print(flat)
+    return flat
