@@ -1,21 +1,20 @@
-// K1 — fused population rollout for sm_100a.
+// K1 — fused population rollout for sm_100a (+ K6 smoothness metric, batched plant step).
 //
-// One thread = one (actor, env) trajectory; one CTA = one actor x up to 128 envs, with that actor's fp32 genome
-// staged once in shared memory.  Per step the CTA runs, entirely on chip:
+// One lane = one (actor, env) trajectory; one warp = 32 envs of one actor; one CTA = 1-2 actors x 128 envs with their
+// fp32 genomes (and the plant tables) staged once in shared memory.  Per step a warp runs, entirely on chip:
 //   Actor.select_action  (base/core/genetic_agent.py:104-109; LayerNorm base/core/mod_utils.py:47-50)        fp32
 //   CitationEnv.step     (envs/phlabenv.py:430-482: action scaling :62-73, fault shims envs/{be,jr,sa,se}/citation.py,
 //                         reward :362-367, termination + penalty :391-399)                                fp64
 //   native plant step    (envs/<variant>/_citation*.so step @0x6030: 6-stage Dormand-Prince ode5, h = 0.01, RHS
-//                         generated from the binary by tools/lift -> csrc/gen/plant_rhs_<variant>.h)          fp64
+//                         generated from the binary by tools/lift -> csrc/gen/plant_rhs_{common,ice}.h)      fp64
 // and accumulates the episodic return (base/core/agent.py:129).  HBM is touched only at episode start
-// (genome, reference-signal parameters) and end (return, step count) unless a trace is requested.
+// (genome, reference-signal parameters) and end (return, step count) unless a trace / action history is requested.
 //
 // Two actor implementations:
-//   rollout_kernel_warp<H>  warp-autonomous: a warp owns 32 envs of one actor and never synchronises with other
-//                           warps.  The MLP is a register-tiled GEMM inside the warp (lane = 1/4 of the output neurons
-//                           x 4 envs, activations exchanged with warp shuffles, weights broadcast from shared memory);
-//                           plant tables live in shared memory next to the genomes.  (h in {32,64,72,96,128})
-//   rollout_kernel_simple   every thread runs the whole MLP for its env (any h that fits); reference / fallback shape.
+//   rollout_kernel_warp<H>  warp-autonomous: a warp never synchronises with other warps.  The MLP is a register-tiled
+//                           GEMM inside the warp (lane = 1/4 of the output neurons x 4 envs, packed FFMA2, activations
+//                           exchanged with warp shuffles, weights broadcast from shared memory).  (h in {32,64,72,96,128})
+//   rollout_kernel_simple   every thread runs the whole MLP for its env (any h that fits); cross-check / fallback shape.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
