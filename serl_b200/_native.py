@@ -5,7 +5,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libserl_b200.so')
+LIB_PATH = os.environ.get('SERL_B200_LIB') or os.path.join(HERE, 'libserl_b200.so')   # SERL_B200_LIB: e.g. the --exact validation build
 
 
 class ActorShape(ctypes.Structure):

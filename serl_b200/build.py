@@ -23,16 +23,24 @@ def _deps():
     return out
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, exact=False):
+    """exact=True builds the validation variant libserl_b200_exact.so (reference operation order in the device plant:
+    csrc/gen_exact, library math, --fmad=false); select it at run time with SERL_B200_LIB=<path>."""
+    if exact:
+        return _build(os.path.join(HERE, 'libserl_b200_exact.so'), ['-DPLANT_EXACT', '--fmad=false'], 'build_exact', force, verbose)
+    return _build(LIB, [], 'build', force, verbose)
+
+
+def _build(LIB, extra, bdir, force, verbose):
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= max(os.path.getmtime(d) for d in _deps()):
         return LIB
     nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
     objs = []
-    os.makedirs(os.path.join(HERE, 'build'), exist_ok=True)
+    os.makedirs(os.path.join(HERE, bdir), exist_ok=True)
     log = []
     for src in SOURCES:
-        obj = os.path.join(HERE, 'build', src.replace('.cu', '.o').replace('.cpp', '.o'))
-        cmd = [nvcc] + NVCC_FLAGS + ['-c', os.path.join(CSRC, src), '-o', obj]
+        obj = os.path.join(HERE, bdir, src.replace('.cu', '.o').replace('.cpp', '.o'))
+        cmd = [nvcc] + NVCC_FLAGS + extra + ['-c', os.path.join(CSRC, src), '-o', obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         log.append(r.stderr)
         if r.returncode != 0:
@@ -43,7 +51,7 @@ def build(force=False, verbose=False):
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError('link failed')
-    with open(os.path.join(HERE, 'build', 'ptxas.log'), 'w') as f:
+    with open(os.path.join(HERE, bdir, 'ptxas.log'), 'w') as f:
         f.write('\n'.join(log))
     if verbose:
         print('\n'.join(log))
@@ -51,4 +59,4 @@ def build(force=False, verbose=False):
 
 
 if __name__ == '__main__':
-    print(build(force=True, verbose='-v' in sys.argv))
+    print(build(force=True, verbose='-v' in sys.argv, exact='--exact' in sys.argv))

@@ -84,12 +84,25 @@ __device__ __forceinline__ void plant_sincos_fast(double x, double* sp, double* 
 }
 __device__ __forceinline__ double plant_sin_fast(double x) { double s, c; plant_sincos_fast(x, &s, &c); return s; }
 __device__ __forceinline__ double plant_cos_fast(double x) { double s, c; plant_sincos_fast(x, &s, &c); return c; }
+#ifdef PLANT_EXACT
+// validation build (`python -m serl_b200.build --exact`): reference operation order, library math, no FMA contraction
+#define PLANT_GEN(f) PLANT_STR(gen_exact/f)
+#define PLANT_DIV(a, b) ((a) / (b))
+#define PLANT_SQRT sqrt
+#define PLANT_FABS fabs
+#define PLANT_SIN sin
+#define PLANT_COS cos
+#define PLANT_SINCOS sincos
+#else
+#define PLANT_GEN(f) PLANT_STR(gen/f)
 #define PLANT_DIV(a, b) plant_div_fast((a), (b))
 #define PLANT_SQRT plant_sqrt_fast
 #define PLANT_FABS fabs
 #define PLANT_SIN plant_sin_fast
 #define PLANT_COS plant_cos_fast
 #define PLANT_SINCOS plant_sincos_fast
+#endif
+#define PLANT_STR(x) #x
 #define PLANT_TAN tan
 #define PLANT_EXP exp
 #define PLANT_LOG10 log10
@@ -98,18 +111,18 @@ __device__ __forceinline__ double plant_cos_fast(double x) { double s, c; plant_
 #include "plant_support.h"
 #undef PLANT_FN
 #define PLANT_FN static __device__ __noinline__
-#include "gen/plant_tables_blob.h"
+#include PLANT_GEN(plant_tables_blob.h)
 #define PLANT_CONSTS(n) static __constant__ double plant_k[n]
 #define PLANT_K(i) plant_k[i]
-#include "gen/plant_consts.h"
+#include PLANT_GEN(plant_consts.h)
 #define PLANT_IC(v) static __device__ const double plant_ic_unused_##v[19]
 #define PLANT_IC_TABLE static __device__ const double plant_ic_table[SERL_PLANT_COUNT][19]
 #define PLANT_PV_TABLE static __device__ const double plant_pv[SERL_PLANT_COUNT][PLANT_NPV]
 #define PLANT_PV(k) plant_pvrow[k]
-#include "gen/plant_ic.h"
-#include "gen/plant_rhs_common.h"     // h2000_v90, cg, cg_for, h2000_v150, h10000_v90: one function + parameter rows
-#include "gen/plant_rhs_ice.h"        // structurally different build
-#include "gen/plant_rhs_nav.h"
+#include PLANT_GEN(plant_ic.h)
+#include PLANT_GEN(plant_rhs_common.h)     // h2000_v90, cg, cg_for, h2000_v150, h10000_v90: one function + parameter rows
+#include PLANT_GEN(plant_rhs_ice.h)        // structurally different build
+#include PLANT_GEN(plant_rhs_nav.h)
 
 #define ROLLOUT_THREADS 128
 #define NX 19
