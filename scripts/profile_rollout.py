@@ -12,10 +12,15 @@ ap.add_argument('--horizon', type=int, default=200)
 ap.add_argument('--iters', type=int, default=3)
 ap.add_argument('--mixed', action='store_true')
 ap.add_argument('--sorted', action='store_true')
+ap.add_argument('--hidden', type=int, default=72)
 a = ap.parse_args()
 dev = torch.device('cuda:0')
-sh = rollout.actor_shape(72)
-w = torch.from_numpy(bench.population(a.pop)).to(dev)
+sh = rollout.actor_shape(a.hidden)
+if a.hidden == 72:
+    w = torch.from_numpy(bench.population(a.pop)).to(dev)
+else:
+    base = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden', 'actors.npz'))['serl50_pop8_h32_tanh']
+    w = torch.from_numpy(np.ascontiguousarray(base[np.arange(a.pop) % 8])).to(dev)
 lv, st = refsig.make_ref_params(a.envs)
 modes = ['nominal'] * a.envs
 if a.mixed:

@@ -839,7 +839,11 @@ extern "C" int serl_rollout(const float* d_weights, int32_t pop, const serl_acto
         // with the tables in shared memory when that fits; else (h = 128) one actor and the tables through L1
         const bool two = (size_t)PT_TOTAL * 8 + 2ull * P4 * 4 <= 227 * 1024 && pop > 1;
         const bool tabs = (size_t)PT_TOTAL * 8 + (size_t)P4 * 4 <= 227 * 1024;
-        if (H == 32) e = two ? launch_warp<32, 2, true>(ar, s) : launch_warp<32, 1, true>(ar, s);
+        static int apc_exp = -1;          // experiment knob (SERL_ROLLOUT_APC=3|4, h = 32 only): more resident warps per SM
+        if (apc_exp < 0) { const char* v = getenv("SERL_ROLLOUT_APC"); apc_exp = v ? atoi(v) : 0; }
+        if (H == 32 && apc_exp == 3 && pop > 2) e = launch_warp<32, 3, true>(ar, s);
+        else if (H == 32 && apc_exp == 4 && pop > 3) e = launch_warp<32, 4, true>(ar, s);
+        else if (H == 32) e = two ? launch_warp<32, 2, true>(ar, s) : launch_warp<32, 1, true>(ar, s);
         else if (H == 64) e = two ? launch_warp<64, 2, true>(ar, s) : launch_warp<64, 1, true>(ar, s);
         else if (H == 72) e = two ? launch_warp<72, 2, true>(ar, s) : launch_warp<72, 1, true>(ar, s);
         else if (H == 96) e = launch_warp<96, 1, true>(ar, s);
