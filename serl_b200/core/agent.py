@@ -69,19 +69,19 @@ class Agent:
         rewards = [float(r) for r in tr[:n, 15]]
         actions = tr[:n, 12:15].copy()
         if store_transition:
-            obs = np.hstack((np.zeros(3), x_ic[[0, 1, 2, 4]]))
-            V0 = x_ic[3]
-            for k in range(n):
-                x = tr[k, 0:12]
-                next_obs = np.hstack((tr[k, 19:22], x[[0, 1, 2, 4]]))
-                done = float(k == n - 1)
-                transition = (obs, tr[k, 16:19], next_obs, rewards[k], done)
-                self.replay_buffer.add(*transition)
-                agent.buffer.add(*transition)
-                cost = (np.rad2deg(np.abs(x[4])) > 11.0 or np.rad2deg(np.abs(x[6])) > 0.75 * self.env.max_phi or x[3] < V0 / 3)
-                if cost:
-                    agent.critical_buffer.add(*transition)
-                obs = next_obs
+            # transitions (obs, action, next_obs, reward, done) of agent.py:101-112, rebuilt from the trace in one shot
+            x = tr[:n, 0:12]
+            next_obs = np.hstack((tr[:n, 19:22], x[:, [0, 1, 2, 4]]))
+            obs = np.vstack((np.hstack((np.zeros(3), x_ic[[0, 1, 2, 4]]))[None], next_obs[:-1]))
+            done = np.zeros(n); done[-1] = 1.0
+            rew = np.asarray(rewards)
+            batch = (obs, tr[:n, 16:19], next_obs, rew, done)
+            self.replay_buffer.add_batch(*batch)
+            agent.buffer.add_batch(*batch)
+            # get_cost (phlabenv.py:369-375, incl. its degrees-vs-radians comparison on the bank angle)
+            cost = (np.rad2deg(np.abs(x[:, 4])) > 11.0) | (np.rad2deg(np.abs(x[:, 6])) > 0.75 * self.env.max_phi) | (x[:, 3] < x_ic[3] / 3)
+            if cost.any():
+                agent.critical_buffer.add_batch(*(b[cost] for b in batch))
             self.num_frames += n
             self.gen_frames += n
             self.num_episodes += 1

@@ -32,6 +32,22 @@ class ReplayMemory:
         self.position = (self.position + 1) % self.capacity
         self._count += 1
 
+    def add_batch(self, states, actions, next_states, rewards, dones):
+        """vectorised `add` of n transitions in order (what a traced GPU episode delivers): same ring semantics."""
+        cols = [np.asarray(v, dtype=np.float32).reshape(len(rewards), -1) for v in (states, actions, next_states, rewards, dones)]
+        n = cols[0].shape[0]
+        if n == 0:
+            return
+        if self._store is None:
+            self._store = {f: np.zeros((self.capacity, c.shape[1]), dtype=np.float32) for f, c in zip(Transition._fields, cols)}
+        idx = (self.position + np.arange(n)) % self.capacity
+        if n > self.capacity:                       # only the last `capacity` rows survive, at the slots they would land in
+            idx, cols = idx[-self.capacity:], [c[-self.capacity:] for c in cols]
+        for f, c in zip(Transition._fields, cols):
+            self._store[f][idx] = c
+        self.position = int((self.position + n) % self.capacity)
+        self._count += n
+
     def _chronological(self):
         n = len(self)
         if self._count <= self.capacity:
