@@ -109,3 +109,23 @@ def test_capi_argument_errors_are_reported():
     with pytest.raises(_native.NativeError):
         _native.check(rc, 'serl_rollout')
     assert L.serl_ssne_select(None, 4, None, 0, None, None, None) == -1
+
+
+@pytest.mark.parametrize('pop,n_envs,hidden,key', [(50, 64, 32, 'serl50_pop8_h32_tanh'), (512, 128, 72, 'serl10_pop_h72_tanh')])
+def test_baseline_config_sizes_through_size_independent_properties(pop, n_envs, hidden, key):
+    """BASELINE configs 2 and 3 at full size (too big for the oracle): determinism, duplicate genomes -> duplicate rows,
+    env-permutation equivariance (returns columns permute exactly), fitness = row mean, step bounds."""
+    base = ACT[key]
+    w = base[np.arange(pop) % base.shape[0]].copy()
+    lv, st = refsig.make_ref_params(n_envs, seed_base=31337)
+    modes = ['nominal'] * n_envs
+    r1 = run(w, hidden, lv, st, modes)
+    ret, stp = r1.returns.cpu().numpy(), r1.steps.cpu().numpy()
+    assert np.isfinite(ret).all() and (stp >= 1).all() and (stp <= 2001).all()
+    nb = base.shape[0]
+    assert np.array_equal(ret[:nb], ret[nb:2 * nb]) and np.array_equal(stp[:nb], stp[nb:2 * nb])      # duplicated genomes
+    assert np.allclose(r1.fitness.cpu().numpy(), ret.mean(1), rtol=1e-12, atol=0)
+    perm = np.random.RandomState(0).permutation(n_envs)
+    r2 = run(w, hidden, lv[perm], st[perm], modes)
+    assert np.array_equal(r2.returns.cpu().numpy(), ret[:, perm])                                    # equivariance + determinism
+    assert np.array_equal(r2.steps.cpu().numpy(), stp[:, perm])
