@@ -23,9 +23,11 @@ def _deps():
     return out
 
 
-def build(force=False, verbose=False, exact=False):
+def build(force=False, verbose=False, exact=False, f32=False):
     """exact=True builds the validation variant libserl_b200_exact.so (reference operation order in the device plant:
     csrc/gen_exact, library math, --fmad=false); select it at run time with SERL_B200_LIB=<path>."""
+    if f32:      # experimental: single-precision right-hand side (csrc/gen_f32)
+        return _build(os.path.join(HERE, 'libserl_b200_f32.so'), ['-DPLANT_F32'], 'build_f32', force, verbose)
     if exact:
         return _build(os.path.join(HERE, 'libserl_b200_exact.so'), ['-DPLANT_EXACT', '--fmad=false'], 'build_exact', force, verbose)
     return _build(LIB, [], 'build', force, verbose)
@@ -59,4 +61,4 @@ def _build(LIB, extra, bdir, force, verbose):
 
 
 if __name__ == '__main__':
-    print(build(force=True, verbose='-v' in sys.argv, exact='--exact' in sys.argv))
+    print(build(force=True, verbose='-v' in sys.argv, exact='--exact' in sys.argv, f32='--f32' in sys.argv))

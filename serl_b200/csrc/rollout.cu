@@ -24,11 +24,15 @@
 #include "../../include/serl_b200.h"
 #include "common.cuh"
 
+#ifdef PLANT_F32
+typedef float real;      // experimental build: single-precision right-hand side, double-precision integrator state
+#else
 typedef double real;
+#endif
 // lookup tables: one blob (gen/plant_tables_blob.h) that the kernels stage into shared memory; the generated
 // right-hand sides address it through the `plant_tab` pointer they are handed.
 #define PLANT_TAB(name) (plant_tab + PT_OFF_##name)
-#define PLANT_XARGS , const double* __restrict__ plant_tab
+#define PLANT_XARGS , const real* __restrict__ plant_tab
 // ---- fast fp64 math for the device plant (<= ~1 ulp; the oracle keeps the reference's exact operations) -------
 // division: 20-bit hardware reciprocal seed + two Newton steps + one residual correction (9 instructions instead of ~33)
 __device__ __forceinline__ double plant_div_fast(double a, double b)
@@ -84,7 +88,20 @@ __device__ __forceinline__ void plant_sincos_fast(double x, double* sp, double* 
 }
 __device__ __forceinline__ double plant_sin_fast(double x) { double s, c; plant_sincos_fast(x, &s, &c); return s; }
 __device__ __forceinline__ double plant_cos_fast(double x) { double s, c; plant_sincos_fast(x, &s, &c); return c; }
-#ifdef PLANT_EXACT
+#if defined(PLANT_F32)
+// experimental build (`python -m serl_b200.build --f32`): fp32 right-hand side (BASELINE north_star: "fp32 ODE integration")
+#define PLANT_GEN(f) PLANT_STR(gen_f32/f)
+#define PLANT_DIV(a, b) ((a) / (b))
+#define PLANT_SQRT sqrtf
+#define PLANT_FABS fabsf
+#define PLANT_SIN sinf
+#define PLANT_COS cosf
+#define PLANT_SINCOS sincosf
+#define PLANT_TAN tanf
+#define PLANT_EXP expf
+#define PLANT_LOG10 log10f
+#define PLANT_POW powf
+#elif defined(PLANT_EXACT)
 // validation build (`python -m serl_b200.build --exact`): reference operation order, library math, no FMA contraction
 #define PLANT_GEN(f) PLANT_STR(gen_exact/f)
 #define PLANT_DIV(a, b) ((a) / (b))
@@ -102,22 +119,24 @@ __device__ __forceinline__ double plant_cos_fast(double x) { double s, c; plant_
 #define PLANT_COS plant_cos_fast
 #define PLANT_SINCOS plant_sincos_fast
 #endif
-#define PLANT_STR(x) #x
+#ifndef PLANT_F32
 #define PLANT_TAN tan
 #define PLANT_EXP exp
 #define PLANT_LOG10 log10
 #define PLANT_POW pow
+#endif
+#define PLANT_STR(x) #x
 #define PLANT_FN static __device__ __forceinline__
 #include "plant_support.h"
 #undef PLANT_FN
 #define PLANT_FN static __device__ __noinline__
 #include PLANT_GEN(plant_tables_blob.h)
-#define PLANT_CONSTS(n) static __constant__ double plant_k[n]
+#define PLANT_CONSTS(n) static __constant__ real plant_k[n]
 #define PLANT_K(i) plant_k[i]
 #include PLANT_GEN(plant_consts.h)
 #define PLANT_IC(v) static __device__ const double plant_ic_unused_##v[19]
 #define PLANT_IC_TABLE static __device__ const double plant_ic_table[SERL_PLANT_COUNT][19]
-#define PLANT_PV_TABLE static __device__ const double plant_pv[SERL_PLANT_COUNT][PLANT_NPV]
+#define PLANT_PV_TABLE static __device__ const real plant_pv[SERL_PLANT_COUNT][PLANT_NPV]
 #define PLANT_PV(k) plant_pvrow[k]
 #include PLANT_GEN(plant_ic.h)
 #include PLANT_GEN(plant_rhs_common.h)     // h2000_v90, cg, cg_for, h2000_v150, h10000_v90: one function + parameter rows
@@ -129,7 +148,7 @@ __device__ __forceinline__ double plant_cos_fast(double x) { double s, c; plant_
 
 // live continuous states of the plant: p q r V alpha beta phi theta | h | washout | N1 N1 N2 N2
 // (psi, x_e, y_e never feed back and are integrated only for traces; Parameter_CSTATE(_g) are folded constants).
-__device__ __forceinline__ void plant_rhs(int variant, const double* X, const double* U, double* xdot, const double* tab)
+__device__ __forceinline__ void plant_rhs(int variant, const real* X, const real* U, real* xdot, const real* tab)
 {
     if (variant == SERL_PLANT_ICE) plant_rhs_ice(X, U, xdot, tab);
     else plant_rhs_common(X, U, xdot, tab, plant_pv[variant]);
@@ -152,19 +171,20 @@ static __constant__ int c_ode5_live[14] = ODE5_LIVE_INIT;
 
 // trace mode only: psi, x_e, y_e (rtX 8, 10, 11).  Their derivatives depend on the live states alone, so they are
 // integrated after the fact with the same stage states, rebuilt from the stored stage derivatives f[6][NX].
-__device__ __noinline__ void plant_step_nav(double* Xnav, const double* X0, const double (*f)[NX], const double* U, const double* tab)
+__device__ __noinline__ void plant_step_nav(double* Xnav, const double* X0, const real (*f)[NX], const real* U, const real* tab)
 {
     const double h = 0.01;
     const int NAV[3] = {8, 10, 11};
-    double g[6][3], xs[NX], xd[NX];
+    double g[6][3], xs[NX];
+    real xr[NX], xd[NX];
 #pragma unroll 1
     for (int s = 0; s < 6; ++s) {
         for (int i = 0; i < NX; ++i) xs[i] = X0[i];
         if (s > 0) {
             for (int li = 0; li < 14; ++li) {
                 const int i = c_ode5_live[li];
-                double acc = f[0][i] * (h * c_ode5_B[s - 1][0]);
-                for (int j = 1; j < s; ++j) acc += f[j][i] * (h * c_ode5_B[s - 1][j]);
+                double acc = (double)f[0][i] * (h * c_ode5_B[s - 1][0]);
+                for (int j = 1; j < s; ++j) acc += (double)f[j][i] * (h * c_ode5_B[s - 1][j]);
                 xs[i] = X0[i] + acc;
             }
             for (int q = 0; q < 3; ++q) {
@@ -173,8 +193,9 @@ __device__ __noinline__ void plant_step_nav(double* Xnav, const double* X0, cons
                 xs[NAV[q]] = X0[NAV[q]] + acc;
             }
         }
-        plant_rhs_nav(xs, U, xd, tab);
-        g[s][0] = xd[8]; g[s][1] = xd[10]; g[s][2] = xd[11];
+        for (int i = 0; i < NX; ++i) xr[i] = (real)xs[i];
+        plant_rhs_nav(xr, U, xd, tab);
+        g[s][0] = (double)xd[8]; g[s][1] = (double)xd[10]; g[s][2] = (double)xd[11];
     }
     for (int q = 0; q < 3; ++q) {
         double acc = g[0][q] * (h * c_ode5_B[5][0]);
@@ -186,34 +207,38 @@ __device__ __noinline__ void plant_step_nav(double* Xnav, const double* X0, cons
 // Stage loop fully unrolled (every f[j][i] load of a stage is independent, h*B folds to constants); the right-hand
 // sides are __noinline__ calls, so x and the stage derivatives f live in local memory (L1/L2-resident scratch: it is
 // the source of the kernel's DRAM write-back traffic, see profiles/).  A rolled loop with the RHS inlined cuts that
-// traffic 20x but runs 22 % slower (measured), so this form is kept.
-__device__ void plant_step(int variant, double* X, const double* U, const double* tab, bool nav = false)
+// traffic 20x but runs 22 % slower (measured), so this form is kept.  The integrator state and the stage
+// combinations are double in every build; `real` (the type of the right-hand side) is double unless PLANT_F32.
+__device__ void plant_step(int variant, double* X, const double* U, const real* tab, bool nav = false)
 {
     constexpr double h = 0.01;
     constexpr double B[6][6] = ODE5_B_INIT;
     constexpr int LIVE[14] = ODE5_LIVE_INIT;
-    double f[6][NX], x[NX];
+    real f[6][NX], x[NX], u[3];
+    u[0] = (real)U[0]; u[1] = (real)U[1]; u[2] = (real)U[2];
 #pragma unroll
-    for (int i = 0; i < NX; ++i) x[i] = X[i];
+    for (int i = 0; i < NX; ++i) x[i] = (real)X[i];
+    double xl[14];
 #pragma unroll
     for (int s = 0; s < 6; ++s) {
-        plant_rhs(variant, x, U, f[s], tab);
+        plant_rhs(variant, x, u, f[s], tab);
 #pragma unroll
         for (int li = 0; li < 14; ++li) {
             const int i = LIVE[li];
-            double acc = f[0][i] * (h * B[s][0]);
+            double acc = (double)f[0][i] * (h * B[s][0]);
 #pragma unroll
-            for (int j = 1; j <= s; ++j) acc += f[j][i] * (h * B[s][j]);
-            x[i] = X[i] + acc;
+            for (int j = 1; j <= s; ++j) acc += (double)f[j][i] * (h * B[s][j]);
+            xl[li] = X[i] + acc;
+            x[i] = (real)xl[li];
         }
     }
     if (nav) {
         double xn[3];
-        plant_step_nav(xn, X, f, U, tab);
+        plant_step_nav(xn, X, f, u, tab);
         X[8] = xn[0]; X[10] = xn[1]; X[11] = xn[2];
     }
 #pragma unroll
-    for (int li = 0; li < 14; ++li) X[LIVE[li]] = x[LIVE[li]];
+    for (int li = 0; li < 14; ++li) X[LIVE[li]] = xl[li];
 }
 
 __device__ __forceinline__ float act_fn(int act, float x)
@@ -248,7 +273,7 @@ struct RolloutArgs {
 
 struct Env {
     double X[NX];
-    const double* tab;       // plant tables (shared or global memory)
+    const real* tab;         // plant tables (shared or global memory)
     const double* ref_lv;    // this env's reference-signal levels / starts [2][SERL_REF_BLOCKS] (global, read per step)
     const double* ref_st;
     double t, ret, theta_trim;
@@ -591,9 +616,9 @@ rollout_kernel_warp(RolloutArgs ar)
 {
     constexpr int S = 7;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* tab_s = reinterpret_cast<double*>(smem_raw);
+    real* tab_s = reinterpret_cast<real*>(smem_raw);
     float* wbase = reinterpret_cast<float*>(tab_s + (TABS ? PT_TOTAL : 0));
-    const double* tab = TABS ? tab_s : plant_tables_blob;
+    const real* tab = TABS ? tab_s : plant_tables_blob;
     const int L = ar.sh.num_layers;
     const int P4 = (ar.P + 3) & ~3;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -799,7 +824,7 @@ template <int H, int APC, bool TABS>
 static cudaError_t launch_warp(const RolloutArgs& ar, cudaStream_t s)
 {
     const int P4 = (ar.P + 3) & ~3;
-    const size_t smem = (TABS ? (size_t)PT_TOTAL * 8 : 0) + (size_t)APC * P4 * 4;
+    const size_t smem = (TABS ? (size_t)PT_TOTAL * sizeof(real) : 0) + (size_t)APC * P4 * 4;
     cudaError_t e = cudaFuncSetAttribute(rollout_kernel_warp<H, APC, TABS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid((ar.n_envs + ROLLOUT_THREADS - 1) / ROLLOUT_THREADS, (ar.pop + APC - 1) / APC);
@@ -837,14 +862,17 @@ extern "C" int serl_rollout(const float* d_weights, int32_t pop, const serl_acto
     if (warp_ok) {
         // two actors per CTA (8 autonomous warps) when two genomes + the plant tables fit in shared memory; one actor
         // with the tables in shared memory when that fits; else (h = 128) one actor and the tables through L1
-        const bool two = (size_t)PT_TOTAL * 8 + 2ull * P4 * 4 <= 227 * 1024 && pop > 1;
-        const bool tabs = (size_t)PT_TOTAL * 8 + (size_t)P4 * 4 <= 227 * 1024;
+        const bool two = (size_t)PT_TOTAL * sizeof(real) + 2ull * P4 * 4 <= 227 * 1024 && pop > 1;
+        const bool tabs = (size_t)PT_TOTAL * sizeof(real) + (size_t)P4 * 4 <= 227 * 1024;
         static int apc_exp = -1;          // experiment knob (SERL_ROLLOUT_APC=3|4, h = 32 only): more resident warps per SM
         if (apc_exp < 0) { const char* v = getenv("SERL_ROLLOUT_APC"); apc_exp = v ? atoi(v) : 0; }
         if (H == 32 && apc_exp == 3 && pop > 2) e = launch_warp<32, 3, true>(ar, s);
         else if (H == 32 && apc_exp == 4 && pop > 3) e = launch_warp<32, 4, true>(ar, s);
         else if (H == 32) e = two ? launch_warp<32, 2, true>(ar, s) : launch_warp<32, 1, true>(ar, s);
         else if (H == 64) e = two ? launch_warp<64, 2, true>(ar, s) : launch_warp<64, 1, true>(ar, s);
+#ifdef PLANT_F32
+        else if (H == 72 && apc_exp == 3 && pop > 2) e = launch_warp<72, 3, true>(ar, s);   // float tables: three genomes fit
+#endif
         else if (H == 72) e = two ? launch_warp<72, 2, true>(ar, s) : launch_warp<72, 1, true>(ar, s);
         else if (H == 96) e = launch_warp<96, 1, true>(ar, s);
         else e = tabs ? launch_warp<128, 1, true>(ar, s) : launch_warp<128, 1, false>(ar, s);
