@@ -166,6 +166,10 @@ def run_ours(args):
     import torch.distributed as dist
     from serl_b200 import rollout, _native
     from serl_b200 import refsig
+    if not os.path.exists(_native.LIB_PATH):      # normally prebuilt in-tree; build the CUDA extension if it is not there
+        if int(os.environ.get('LOCAL_RANK', '0')) == 0:
+            from serl_b200 import build as _b
+            _b.build()
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
