@@ -170,6 +170,11 @@ def run_ours(args):
         if int(os.environ.get('LOCAL_RANK', '0')) == 0:
             from serl_b200 import build as _b
             _b.build()
+        else:
+            for _ in range(600):
+                if os.path.exists(_native.LIB_PATH):
+                    break
+                time.sleep(0.5)
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
