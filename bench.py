@@ -307,6 +307,30 @@ def run_ours(args):
         del r, sm
         launches_note = 'rollout + fitness_mean per step; a generation adds K2 + K3..K5 launches'
 
+    extras = None
+    if world == 1 and not args.no_generation:
+        def timed_rollout(genomes, modes_t):
+            a0 = torch.cuda.Event(enable_timing=True); a1 = torch.cuda.Event(enable_timing=True)
+            rollout.population_rollout(genomes, sh, lv, st, modes_t, horizon=HORIZON)       # warm
+            a0.record()
+            rr = rollout.population_rollout(genomes, sh, lv, st, modes_t, horizon=HORIZON)
+            a1.record(); torch.cuda.synchronize()
+            n = int(rr.steps.sum().item())
+            return {'executed_env_steps': n, 'ms': a0.elapsed_time(a1), 'env_steps_per_sec': n / (a0.elapsed_time(a1) * 1e-3),
+                    'mean_episode_steps': n / float(rr.steps.numel())}
+        # (i) reference-termination mode: generation-0 (random-init) actors crash early; only executed steps count
+        import types
+        from serl_b200.core import genetic_agent
+        torch.manual_seed(7)
+        a_ns = types.SimpleNamespace(hidden_size=HIDDEN, num_layers=3, activation_actor='tanh', state_dim=7, action_dim=3)
+        w0 = torch.stack([genetic_agent.Actor(a_ns).flat() for _ in range(POP)]).to(dev)
+        extras = {'random_init_population': timed_rollout(w0, md)}
+        # (ii) BASELINE config 4 style: fault / plant mode randomised per env over {nominal, be, jr, sa, se, ice, cg}
+        mrng = np.random.RandomState(7)
+        mixed = [['nominal', 'be', 'jr', 'sa', 'se', 'ice', 'cg'][i] for i in mrng.randint(0, 7, N_ENVS)]
+        md_mixed = torch.tensor([rollout.mode_code(m) for m in mixed], dtype=torch.int32, device=dev)
+        extras['mixed_faults_per_env'] = timed_rollout(w, md_mixed)
+
     if rank == 0:
         peak, how = peaks()
         traffic = None
@@ -327,7 +351,7 @@ def run_ours(args):
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
             'gpu_launches': int(launches),
-            'generation_ms': gen_ms, 'epoch_breakdown': (epoch_timing if gen_ms is not None else None), 'smoothness': smooth_timing,
+            'generation_ms': gen_ms, 'epoch_breakdown': (epoch_timing if gen_ms is not None else None), 'smoothness': smooth_timing, 'other_workloads': extras,
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
                          'peak_source': how, 'kernel': 'rollout_kernel', 'kernel_ms': kern_ms,
                          'note': 'BASELINE metric denominator (208 B/env-step state round-trip model); the kernel keeps state on chip and is '
