@@ -303,7 +303,7 @@ def run_ours(args):
         sm = rollout.smoothness(r.actions, r.steps)
         s2.record(); torch.cuda.synchronize()
         smooth_timing = {'rollout_with_action_history_ms': s0.elapsed_time(s1), 'smoothness_kernel_ms': s1.elapsed_time(s2),
-                         'action_history_bytes': int(r.actions.numel() * 8)}
+                         'action_history_bytes': int(r.actions.numel() * 4)}
         del r, sm
         launches_note = 'rollout + fitness_mean per step; a generation adds K2 + K3..K5 launches'
 

@@ -63,20 +63,20 @@ int64_t serl_actor_num_params(const serl_actor_shape* shape);
  *   d_trace     optional [pop, n_envs, horizon, SERL_TRACE_COLS] f64 per-step record (Episode fields, core/utils.py:12-36):
  *               0-11 state before the step (psi, x_e, y_e are integrated only when a trace is requested),
  *               12-14 commanded deflection last_u, 15 reward, 16-18 action fed to the env, 19-21 tracking error
- *   d_actions   optional [pop, n_envs, horizon, 3] f64: commanded deflection last_u of every executed step (agent.py:98),
- *               the input of the smoothness metric (serl_smoothness)
+ *   d_actions   optional [pop, n_envs, horizon, 3] fp32: commanded deflection last_u of every executed step (agent.py:98),
+ *               the input of the smoothness metric (serl_smoothness, which computes its DFT in fp32)
  */
 #define SERL_TRACE_COLS 22
 int serl_rollout(const float* d_weights, int32_t pop, const serl_actor_shape* shape,
                  const double* d_ref_levels, const double* d_ref_starts, const int32_t* d_env_mode,
                  int32_t n_envs, int32_t horizon, const float* d_action_noise,
-                 double* d_returns, int32_t* d_steps, double* d_fitness, double* d_trace, double* d_actions,
+                 double* d_returns, int32_t* d_steps, double* d_fitness, double* d_trace, float* d_actions,
                  void* stream);
 
 /* K6: action smoothness of n_traj trajectories (base/core/utils.py:82-120 calc_smoothness; agent.py:128-134):
  * out[t] = -sqrt(sum_i sum_k f_k |FFT(y_i)[k]|^2 dt 2/N) * 100 * 80/(N dt) over the N = d_steps[t] executed steps of
  * d_actions [n_traj, horizon, 3]. */
-int serl_smoothness(const double* d_actions, const int32_t* d_steps, int32_t n_traj, int32_t horizon, double dt,
+int serl_smoothness(const float* d_actions, const int32_t* d_steps, int32_t n_traj, int32_t horizon, double dt,
                     double* d_out, void* stream);
 
 /* Native plant, batched (replaces envs/<variant>/citation.py:65-72 initialize()/step() for n independent models).

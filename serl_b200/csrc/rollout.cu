@@ -267,7 +267,7 @@ struct RolloutArgs {
     const double* ref_levels; const double* ref_starts; const int* env_mode; int n_envs; int horizon;
     const float* action_noise;      // optional [pop, n_envs, horizon, 3]: clipped exploration noise (agent.py:90-93)
     double* returns; int* steps; double* trace;   // trace optional [pop, n_envs, horizon, SERL_TRACE_COLS]
-    double* actions;                // optional [pop, n_envs, horizon, 3]: commanded deflection last_u (smoothness metric)
+    float* actions;                 // optional [pop, n_envs, horizon, 3] fp32: commanded deflection last_u (smoothness metric)
     int pop;
 };
 
@@ -357,8 +357,8 @@ __device__ void env_step(Env& e, const RolloutArgs& ar, size_t traj, const float
     if (done) reward += (-1.0 / 0.01) * (20.0 - t) * 2.0;      // check_bounds penalty (:391-399)
     e.ret += reward;
     if (ar.actions) {
-        double* au = ar.actions + (traj * ar.horizon + e.k) * 3;
-        au[0] = U[0]; au[1] = U[1]; au[2] = U[2];
+        float* au = ar.actions + (traj * ar.horizon + e.k) * 3;
+        au[0] = (float)U[0]; au[1] = (float)U[1]; au[2] = (float)U[2];
     }
     if (ar.trace) {
         double* tr = ar.trace + (traj * ar.horizon + e.k) * SERL_TRACE_COLS;
@@ -731,7 +731,7 @@ extern "C" int serl_plant_step(double* d_X, const double* d_cmd, const int32_t* 
 // no radix-2 structure; 12 M fp32 MACs per trajectory), frequency-weighted power summed in double:
 //   S = sum_i sum_{k=1}^{N/2-1} f_k |Y_i[k]|^2 dt * 2/N,  f = linspace(dt, 1/(2dt), N/2-1),  result = -sqrt(S)*100*(80/(N dt)).
 __global__ void __launch_bounds__(256)
-smoothness_kernel(const double* __restrict__ actions, const int* __restrict__ steps, int horizon, double dt, double* __restrict__ out)
+smoothness_kernel(const float* __restrict__ actions, const int* __restrict__ steps, int horizon, double dt, double* __restrict__ out)
 {
     extern __shared__ __align__(16) unsigned char sm_raw[];
     const int traj = blockIdx.x;
@@ -742,12 +742,12 @@ smoothness_kernel(const double* __restrict__ actions, const int* __restrict__ st
     float* y0 = reinterpret_cast<float*>(tw + horizon);       // [3][N]
     float* y1 = y0 + horizon;
     float* y2 = y1 + horizon;
-    const double* a = actions + (size_t)traj * horizon * 3;
+    const float* a = actions + (size_t)traj * horizon * 3;
     for (int n = threadIdx.x; n < N; n += blockDim.x) {
         float sv, cv;
         sincospif(2.0f * (float)n / (float)N, &sv, &cv);
         tw[n] = make_float2(cv, sv);
-        y0[n] = (float)a[3 * n]; y1[n] = (float)a[3 * n + 1]; y2[n] = (float)a[3 * n + 2];
+        y0[n] = a[3 * n]; y1[n] = a[3 * n + 1]; y2[n] = a[3 * n + 2];
     }
     __syncthreads();
     const double fstep = M > 1 ? (1.0 / (2.0 * dt) - dt) / (double)(M - 1) : 0.0;
@@ -797,7 +797,7 @@ smoothness_kernel(const double* __restrict__ actions, const int* __restrict__ st
     }
 }
 
-extern "C" int serl_smoothness(const double* d_actions, const int32_t* d_steps, int32_t n_traj, int32_t horizon, double dt,
+extern "C" int serl_smoothness(const float* d_actions, const int32_t* d_steps, int32_t n_traj, int32_t horizon, double dt,
                                double* d_out, void* stream)
 {
     if (!d_actions || !d_steps || !d_out || n_traj <= 0 || horizon <= 0) return serl_fail(SERL_ERR_ARG, "serl_smoothness: bad argument");
@@ -835,7 +835,7 @@ static cudaError_t launch_warp(const RolloutArgs& ar, cudaStream_t s)
 extern "C" int serl_rollout(const float* d_weights, int32_t pop, const serl_actor_shape* shape,
                             const double* d_ref_levels, const double* d_ref_starts, const int32_t* d_env_mode,
                             int32_t n_envs, int32_t horizon, const float* d_action_noise,
-                            double* d_returns, int32_t* d_steps, double* d_fitness, double* d_trace, double* d_actions, void* stream)
+                            double* d_returns, int32_t* d_steps, double* d_fitness, double* d_trace, float* d_actions, void* stream)
 {
     if (!d_weights || !shape || !d_ref_levels || !d_ref_starts || !d_env_mode || !d_returns || !d_steps)
         return serl_fail(SERL_ERR_ARG, "serl_rollout: null pointer argument");

@@ -74,7 +74,7 @@ def population_rollout(weights, shape, ref_levels, ref_starts, env_mode, horizon
         r.steps = torch.empty((pop, n_envs), dtype=torch.int32, device=dev)
         r.fitness = torch.empty((pop,), dtype=torch.float64, device=dev)
         r.trace = None
-        r.actions = torch.empty((pop, n_envs, horizon, 3), dtype=torch.float64, device=dev) if actions else None
+        r.actions = torch.empty((pop, n_envs, horizon, 3), dtype=torch.float32, device=dev) if actions else None
         if trace:
             r.trace = torch.full((pop, n_envs, horizon, TRACE_COLS), float('nan'), dtype=torch.float64, device=dev)
     stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
@@ -86,12 +86,12 @@ def population_rollout(weights, shape, ref_levels, ref_starts, env_mode, horizon
 
 
 def smoothness(actions, steps, dt=0.01):
-    """K6: per-trajectory action smoothness (core/utils.py calc_smoothness) of `actions` [..., horizon, 3] f64 (cuda) over the
+    """K6: per-trajectory action smoothness (core/utils.py calc_smoothness) of `actions` [..., horizon, 3] fp32 (cuda) over the
     first `steps` [...] executed steps. Returns f64 tensor shaped like `steps`."""
     L = _native.lib()
     horizon = actions.shape[-2]
     n = steps.numel()
-    assert actions.is_cuda and actions.dtype == torch.float64 and actions.is_contiguous() and actions.numel() == n * horizon * 3
+    assert actions.is_cuda and actions.dtype == torch.float32 and actions.is_contiguous() and actions.numel() == n * horizon * 3
     st = steps.contiguous().to(torch.int32)
     out = torch.empty(st.shape, dtype=torch.float64, device=actions.device)
     stream = ctypes.c_void_p(torch.cuda.current_stream(actions.device).cuda_stream)

@@ -143,7 +143,7 @@ def test_smoothness_kernel_matches_reference_formula():
                                    torch.as_tensor(st, device=dev), md, actions=True)
     sm = rollout.smoothness(r.actions, r.steps).cpu().numpy()
     steps = r.steps.cpu().numpy()
-    a = r.actions.cpu().numpy()
+    a = r.actions.cpu().numpy().astype(np.float64)
     assert (steps < 2001).any() and (steps == 2001).any()
     for i in range(4):
         for e in range(3):
