@@ -18,7 +18,7 @@ from typing import Dict
 import numpy as np
 import torch
 
-from . import genetic_agent, mod_utils, replay_memory, td3
+from . import mod_utils, replay_memory, td3
 from . import mod_neuro_evo as utils_ne
 from .utils import Episode, calc_smoothness
 from .. import engine, rollout

@@ -4,9 +4,6 @@ Same constructor and `epoch(pop, fitness_evals, bcs_evals=None) -> int` contract
 PopulationList (its genomes are mutated in place on the GPU).  Only the classic operators are implemented; asking for
 proximal / safe mutation or distillation crossover raises, as the reference does for unknown operators (:38, :507).
 """
-import numpy as np
-import torch
-
 from .. import evo
 
 

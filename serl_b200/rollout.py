@@ -5,7 +5,6 @@ through every environment; fitness[a] = mean over envs of the episodic return.
 """
 import ctypes
 
-import numpy as np
 import torch
 
 from . import _native

@@ -2,7 +2,6 @@
 import os
 
 import numpy as np
-import torch
 
 from oracle import actor as A, phlab, plant as P, refsig
 

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from oracle import actor as A, phlab, plant as P, refsig
+from oracle import actor as A, phlab, refsig
 
 pytestmark = pytest.mark.gpu
 G = os.path.join(os.path.dirname(__file__), 'golden')

@@ -1,6 +1,6 @@
 """Exact (bit-for-bit, IEEE double) evaluator for a traced expression graph; used to check the trace
 against the live reference binary before any code is generated."""
-import ctypes, math, struct
+import ctypes, math
 import symtrace as S
 
 _libm = ctypes.CDLL('libm.so.6')

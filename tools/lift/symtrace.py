@@ -24,7 +24,6 @@ import re
 import shutil
 import struct
 import subprocess
-import sys
 
 M64 = (1 << 64) - 1
 SIGN = 1 << 63

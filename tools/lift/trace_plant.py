@@ -1,5 +1,5 @@
 """Trace xdot = f(X, cmd) out of a plant binary. See symtrace.py."""
-import ctypes, sys, os, pickle, struct
+import ctypes, sys, os
 sys.path.insert(0, os.path.dirname(__file__))
 sys.setrecursionlimit(100000)
 import symtrace as S
