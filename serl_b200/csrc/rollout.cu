@@ -508,9 +508,10 @@ __device__ __forceinline__ float group_sum(float v)
     return v;
 }
 
-template <int H>
-__device__ void actor_forward_warp(const float* __restrict__ w, int L, int actfn, int lane, const float* obs, float* action)
+template <int H, int ACT>
+__device__ __noinline__ void actor_forward_warp(const float* __restrict__ w, int L, int lane, const float* obs, float* action)
 {
+    constexpr int actfn = ACT;
     constexpr int TM = H / 4, TM2 = H / 8;
     constexpr int S = 7, A = 3;
     const int og = lane & 3, gbase = lane & ~3;
@@ -668,8 +669,12 @@ rollout_kernel_warp(RolloutArgs ar)
 #pragma unroll
         for (int i = 0; i < 7; ++i) obs[i] = 0.f; }
     const size_t traj = valid ? (size_t)actor * ar.n_envs + env : 0;
+    const int actfn = ar.sh.activation;
     while (__any_sync(0xffffffffu, !e.done)) {
-        actor_forward_warp<H>(w, L, ar.sh.activation, lane, obs, a);
+        // one instantiation per activation: the choice is compiled into the 4 x h/4 activation calls of every layer
+        if (actfn == SERL_ACT_TANH) actor_forward_warp<H, SERL_ACT_TANH>(w, L, lane, obs, a);
+        else if (actfn == SERL_ACT_ELU) actor_forward_warp<H, SERL_ACT_ELU>(w, L, lane, obs, a);
+        else actor_forward_warp<H, SERL_ACT_LEAKY_RELU>(w, L, lane, obs, a);
         if (!e.done) env_step(e, ar, traj, a, obs);
     }
     if (valid) {
