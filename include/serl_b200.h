@@ -73,6 +73,15 @@ int serl_rollout(const float* d_weights, int32_t pop, const serl_actor_shape* sh
                  double* d_returns, int32_t* d_steps, double* d_fitness, double* d_trace, float* d_actions,
                  void* stream);
 
+/* Same with the episode length and reference-transition width of the reference's evaluation mode
+ * (envs/phlabenv.py:295-301 set_eval_mode: t_max = 80 s; init_ref :303-345: smooth_width = t_max // 6, block_width =
+ * t_max // 5 are encoded in d_ref_starts by the caller); horizon must cover t_max / 0.01 + 1 steps. */
+int serl_rollout_eval(const float* d_weights, int32_t pop, const serl_actor_shape* shape,
+                      const double* d_ref_levels, const double* d_ref_starts, const int32_t* d_env_mode,
+                      int32_t n_envs, int32_t horizon, const float* d_action_noise,
+                      double* d_returns, int32_t* d_steps, double* d_fitness, double* d_trace, float* d_actions,
+                      double t_max, double smooth_width, void* stream);
+
 /* K6: action smoothness of n_traj trajectories (base/core/utils.py:82-120 calc_smoothness; agent.py:128-134):
  * out[t] = -sqrt(sum_i sum_k f_k |FFT(y_i)[k]|^2 dt 2/N) * 100 * 80/(N dt) over the N = d_steps[t] executed steps of
  * d_actions [n_traj, horizon, 3]. */

@@ -15,9 +15,10 @@ DT = 0.01
 class CitationEnv:
     n_actions = 3
     obs_idx = [0, 1, 2, 4]
-    t_max = 20
 
-    def __init__(self, mode='nominal', backend='auto', plant=None):
+    def __init__(self, mode='nominal', backend='auto', plant=None, t_max=20):
+        self.t_max = t_max
+        self.smooth_w = refsig.widths(t_max)[1]
         self.variant, self.fault = P.MODES[mode]
         self.plant = plant if plant is not None else P.make_plant(self.variant, backend)
         self.bound = np.deg2rad(10)
@@ -54,8 +55,8 @@ class CitationEnv:
         return self.obs
 
     def ref_deg(self):
-        return np.array([refsig.ref_value_deg(self.levels[0], self.starts[0], self.t, self.theta_trim),
-                         refsig.ref_value_deg(self.levels[1], self.starts[1], self.t, 0.0), 0.0])
+        return np.array([refsig.ref_value_deg(self.levels[0], self.starts[0], self.t, self.theta_trim, self.smooth_w),
+                         refsig.ref_value_deg(self.levels[1], self.starts[1], self.t, 0.0, self.smooth_w), 0.0])
 
     # phlabenv.py:430-482
     def step(self, action):

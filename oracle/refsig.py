@@ -18,8 +18,14 @@ N_LEVELS = 10
 AMPL = (30.0, 20.0)   # theta, phi [deg]
 
 
-def make_ref_params(n_envs, seed_base=7_000_000):
+def widths(t_max=20):
+    """(block width, smooth width, timing jitter) of init_ref (envs/phlabenv.py:321-335) for an episode of t_max seconds."""
+    return float(t_max // 5), float(t_max // 6), t_max / 500.
+
+
+def make_ref_params(n_envs, seed_base=7_000_000, t_max=20):
     """levels[n_envs, 2, N_BLOCKS] (deg, without the theta trim offset), starts[n_envs, 2, N_BLOCKS] (s)."""
+    block_w, _, jitter = widths(t_max)
     levels = np.zeros((n_envs, 2, N_BLOCKS))
     starts = np.zeros((n_envs, 2, N_BLOCKS))
     for e in range(n_envs):
@@ -28,14 +34,14 @@ def make_ref_params(n_envs, seed_base=7_000_000):
             grid = np.linspace(-AMPL[c], AMPL[c], N_LEVELS)
             lv = grid[rs.randint(0, N_LEVELS, size=N_BLOCKS)]
             lv[0] = 0.0
-            st = BLOCK_W * np.arange(N_BLOCKS) + rs.uniform(-JITTER, JITTER, size=N_BLOCKS)
+            st = block_w * np.arange(N_BLOCKS) + rs.uniform(-jitter, jitter, size=N_BLOCKS)
             st[0] = 0.0
             levels[e, c] = lv
             starts[e, c] = st
     return levels, starts
 
 
-def ref_value_deg(levels, starts, t, offset=0.0):
+def ref_value_deg(levels, starts, t, offset=0.0, smooth_w=SMOOTH_W):
     """value [deg] of one channel at time t. levels/starts: [N_BLOCKS]."""
     k = 0
     for j in range(1, N_BLOCKS):
@@ -43,7 +49,7 @@ def ref_value_deg(levels, starts, t, offset=0.0):
             k = j
     if k == 0:
         return offset + levels[0]
-    x = (t - starts[k]) / SMOOTH_W
+    x = (t - starts[k]) / smooth_w
     if x >= 1.0:
         return offset + levels[k]
     return offset + (levels[k - 1] + (levels[k] - levels[k - 1]) * (0.5 * (1.0 - np.cos(np.pi * x))))

@@ -33,6 +33,8 @@ def lib():
         L.serl_actor_num_params.argtypes = [ctypes.POINTER(ActorShape)]
         L.serl_rollout.restype = ctypes.c_int
         L.serl_rollout.argtypes = [vp, i32, ctypes.POINTER(ActorShape), vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp]
+        L.serl_rollout_eval.restype = ctypes.c_int
+        L.serl_rollout_eval.argtypes = L.serl_rollout.argtypes[:-1] + [ctypes.c_double, ctypes.c_double, vp]
         L.serl_smoothness.restype = ctypes.c_int
         L.serl_smoothness.argtypes = [vp, vp, i32, i32, ctypes.c_double, vp, vp]
         L.serl_launch_count.restype = i64

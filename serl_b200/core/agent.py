@@ -21,7 +21,7 @@ import torch
 from . import mod_utils, replay_memory, td3
 from . import mod_neuro_evo as utils_ne
 from .utils import Episode, calc_smoothness
-from .. import engine, rollout
+from .. import engine, refsig, rollout
 from ..population import PopulationList
 
 
@@ -107,10 +107,13 @@ class Agent:
             # one np.random.randn(3) per executed step (agent.py:90-93): draw a full horizon, then rewind the global
             # stream to "exactly the steps that ran" once the episode length is known
             state = np.random.get_state()
-            z = np.random.randn(rollout.HORIZON, 3)
+            z = np.random.randn(int(round(env.t_max / env.dt)) + 1, 3)
             clipped = np.clip(self.args.noise_sd * z, -self.args.noise_clip, self.args.noise_clip)
-            noise = torch.as_tensor(clipped.astype(np.float32).reshape(1, 1, rollout.HORIZON, 3), device=self.device)
-        r = rollout.population_rollout(self._genome_of(agent), self.shape, lv, st, md, trace=True, action_noise=noise)
+            noise = torch.as_tensor(clipped.astype(np.float32).reshape(1, 1, -1, 3), device=self.device)
+        horizon = int(round(env.t_max / env.dt)) + 1
+        kw = {} if env.t_max == 20 else {'t_max': float(env.t_max), 'smooth_width': refsig.widths(env.t_max)[1]}
+        r = rollout.population_rollout(self._genome_of(agent), self.shape, lv, st, md, trace=True, action_noise=noise,
+                                       horizon=horizon, **kw)
         n = int(r.steps[0, 0].item())
         tr = r.trace[0, 0, :n].cpu().numpy()
         if is_action_noise:
@@ -119,7 +122,8 @@ class Agent:
         x_ic = self._initial_state(env)
         theta_trim = np.rad2deg(x_ic[7])
         from ..envs.phlabenv import _RefSignal
-        refs = [_RefSignal(levels[0], starts[0], theta_trim), _RefSignal(levels[1], starts[1], 0.0), lambda t: 0.0]
+        sw = refsig.widths(env.t_max)[1]
+        refs = [_RefSignal(levels[0], starts[0], theta_trim, sw), _RefSignal(levels[1], starts[1], 0.0, sw), lambda t: 0.0]
         return self._episode_from_trace(agent, tr, n, x_ic, store_transition, refs)
 
     _ic_cache: Dict[int, np.ndarray] = {}

@@ -249,14 +249,14 @@ __device__ __forceinline__ float act_fn(int act, float x)
 }
 
 // reference-signal value in degrees (serl_b200/refsig.py; recovered shape of signals.RandomizedCosineStepSequence)
-__device__ __forceinline__ double ref_deg(const double* __restrict__ lv, const double* __restrict__ st, double t, double offset)
+__device__ __forceinline__ double ref_deg(const double* __restrict__ lv, const double* __restrict__ st, double t, double offset, double smooth_w)
 {
     int k = 0;
 #pragma unroll
     for (int j = 1; j < SERL_REF_BLOCKS; ++j)
         if (t >= st[j]) k = j;
     if (k == 0) return offset + lv[0];
-    const double x = (t - st[k]) / 3.0;
+    const double x = (t - st[k]) / smooth_w;
     if (x >= 1.0) return offset + lv[k];
     return offset + (lv[k - 1] + (lv[k] - lv[k - 1]) * (0.5 * (1.0 - cos(3.141592653589793 * x))));
 }
@@ -269,6 +269,8 @@ struct RolloutArgs {
     double* returns; int* steps; double* trace;   // trace optional [pop, n_envs, horizon, SERL_TRACE_COLS]
     float* actions;                 // optional [pop, n_envs, horizon, 3] fp32: commanded deflection last_u (smoothness metric)
     int pop;
+    double t_max;                   // episode length [s] (envs/phlabenv.py:181; 80 in evaluation mode :295-301)
+    double smooth_w;                // width of the raised-cosine reference transitions [s] (t_max // 6)
 };
 
 struct Env {
@@ -346,15 +348,15 @@ __device__ void env_step(Env& e, const RolloutArgs& ar, size_t traj, const float
     plant_step(e.variant, e.X, cmd, e.tab, ar.trace != nullptr);
 
     const double t = e.t;
-    const double r_th = ref_deg(e.ref_lv, e.ref_st, t, e.theta_trim) * DEG2RAD;
-    const double r_ph = ref_deg(e.ref_lv + SERL_REF_BLOCKS, e.ref_st + SERL_REF_BLOCKS, t, 0.0) * DEG2RAD;
+    const double r_th = ref_deg(e.ref_lv, e.ref_st, t, e.theta_trim, ar.smooth_w) * DEG2RAD;
+    const double r_ph = ref_deg(e.ref_lv + SERL_REF_BLOCKS, e.ref_st + SERL_REF_BLOCKS, t, 0.0, ar.smooth_w) * DEG2RAD;
     const double e0 = r_th - xo[7], e1 = r_ph - xo[6], e2 = 0.0 - xo[5];
     const double c0 = fabs(fmin(fmax(k_err * e0, -1.0), 1.0));
     const double c1 = fabs(fmin(fmax(k_err * e1, -1.0), 1.0));
     const double c2 = fabs(fmin(fmax(k_err4 * e2, -1.0), 1.0));
     double reward = -((c0 + c1) + c2) / 3.0;
-    const bool done = (t >= 20.0) || (fabs(xo[7]) > max_theta) || (fabs(xo[6]) > max_phi) || (xo[9] < 50.0);
-    if (done) reward += (-1.0 / 0.01) * (20.0 - t) * 2.0;      // check_bounds penalty (:391-399)
+    const bool done = (t >= ar.t_max) || (fabs(xo[7]) > max_theta) || (fabs(xo[6]) > max_phi) || (xo[9] < 50.0);
+    if (done) reward += (-1.0 / 0.01) * (ar.t_max - t) * 2.0;  // check_bounds penalty (:391-399)
     e.ret += reward;
     if (ar.actions) {
         float* au = ar.actions + (traj * ar.horizon + e.k) * 3;
@@ -839,10 +841,37 @@ static cudaError_t launch_warp(const RolloutArgs& ar, cudaStream_t s)
     return cudaGetLastError();
 }
 
+static int rollout_impl(const float* d_weights, int32_t pop, const serl_actor_shape* shape,
+                        const double* d_ref_levels, const double* d_ref_starts, const int32_t* d_env_mode,
+                        int32_t n_envs, int32_t horizon, const float* d_action_noise,
+                        double* d_returns, int32_t* d_steps, double* d_fitness, double* d_trace, float* d_actions,
+                        double t_max, double smooth_w, void* stream);
+
 extern "C" int serl_rollout(const float* d_weights, int32_t pop, const serl_actor_shape* shape,
                             const double* d_ref_levels, const double* d_ref_starts, const int32_t* d_env_mode,
                             int32_t n_envs, int32_t horizon, const float* d_action_noise,
                             double* d_returns, int32_t* d_steps, double* d_fitness, double* d_trace, float* d_actions, void* stream)
+{
+    return rollout_impl(d_weights, pop, shape, d_ref_levels, d_ref_starts, d_env_mode, n_envs, horizon, d_action_noise,
+                        d_returns, d_steps, d_fitness, d_trace, d_actions, 20.0, 3.0, stream);
+}
+
+extern "C" int serl_rollout_eval(const float* d_weights, int32_t pop, const serl_actor_shape* shape,
+                                 const double* d_ref_levels, const double* d_ref_starts, const int32_t* d_env_mode,
+                                 int32_t n_envs, int32_t horizon, const float* d_action_noise,
+                                 double* d_returns, int32_t* d_steps, double* d_fitness, double* d_trace, float* d_actions,
+                                 double t_max, double smooth_width, void* stream)
+{
+    if (!(t_max > 0.0) || !(smooth_width > 0.0)) return serl_fail(SERL_ERR_ARG, "serl_rollout_eval: t_max and smooth_width must be > 0");
+    return rollout_impl(d_weights, pop, shape, d_ref_levels, d_ref_starts, d_env_mode, n_envs, horizon, d_action_noise,
+                        d_returns, d_steps, d_fitness, d_trace, d_actions, t_max, smooth_width, stream);
+}
+
+static int rollout_impl(const float* d_weights, int32_t pop, const serl_actor_shape* shape,
+                        const double* d_ref_levels, const double* d_ref_starts, const int32_t* d_env_mode,
+                        int32_t n_envs, int32_t horizon, const float* d_action_noise,
+                        double* d_returns, int32_t* d_steps, double* d_fitness, double* d_trace, float* d_actions,
+                        double t_max, double smooth_w, void* stream)
 {
     if (!d_weights || !shape || !d_ref_levels || !d_ref_starts || !d_env_mode || !d_returns || !d_steps)
         return serl_fail(SERL_ERR_ARG, "serl_rollout: null pointer argument");
@@ -860,7 +889,7 @@ extern "C" int serl_rollout(const float* d_weights, int32_t pop, const serl_acto
     RolloutArgs ar;
     ar.weights = d_weights; ar.P = (int)serl_actor_num_params(shape); ar.sh = *shape;
     ar.ref_levels = d_ref_levels; ar.ref_starts = d_ref_starts; ar.env_mode = d_env_mode; ar.n_envs = n_envs; ar.horizon = horizon;
-    ar.action_noise = d_action_noise; ar.returns = d_returns; ar.steps = d_steps; ar.trace = d_trace; ar.actions = d_actions; ar.pop = pop;
+    ar.action_noise = d_action_noise; ar.returns = d_returns; ar.steps = d_steps; ar.trace = d_trace; ar.actions = d_actions; ar.pop = pop; ar.t_max = t_max; ar.smooth_w = smooth_w;
     const int P4 = (ar.P + 3) & ~3;
     const int H = shape->hidden;
     dim3 grid((n_envs + ROLLOUT_THREADS - 1) / ROLLOUT_THREADS, pop);

@@ -25,11 +25,11 @@ class Box:
 
 
 class _RefSignal:
-    def __init__(self, levels, starts, offset):
-        self.levels, self.starts, self.offset = levels, starts, offset
+    def __init__(self, levels, starts, offset, smooth_w=refsig.SMOOTH_W):
+        self.levels, self.starts, self.offset, self.smooth_w = levels, starts, offset, smooth_w
 
     def __call__(self, t):
-        return refsig.ref_value_deg(self.levels, self.starts, t, self.offset)
+        return refsig.ref_value_deg(self.levels, self.starts, t, self.offset, self.smooth_w)
 
 
 class CitationEnv:
@@ -110,6 +110,11 @@ class CitationEnv:
         return low + 0.5 * (clipped_action + 1.0) * (high - low)
 
     # ---- reference signals ----
+    def set_eval_mode(self, t_max: int = 80) -> None:
+        """envs/phlabenv.py:295-301: longer evaluation episodes (reference widths scale with t_max, :321-335)."""
+        self.t_max = int(t_max)
+        self.eval_mode = True
+
     def draw_reference(self):
         """consume the global np.random stream like init_ref (:303-345) and return (levels[2,6], starts[2,6])."""
         levels = np.zeros((2, refsig.N_BLOCKS))
@@ -118,7 +123,8 @@ class CitationEnv:
             grid = np.linspace(-refsig.AMPL[c], refsig.AMPL[c], refsig.N_LEVELS)
             lv = grid[np.random.randint(0, refsig.N_LEVELS, size=refsig.N_BLOCKS)]
             lv[0] = 0.0
-            st = refsig.BLOCK_W * np.arange(refsig.N_BLOCKS) + np.random.uniform(-refsig.JITTER, refsig.JITTER, size=refsig.N_BLOCKS)
+            block_w, _, jitter = refsig.widths(self.t_max)
+            st = block_w * np.arange(refsig.N_BLOCKS) + np.random.uniform(-jitter, jitter, size=refsig.N_BLOCKS)
             st[0] = 0.0
             levels[c], starts[c] = lv, st
         return levels, starts
@@ -126,8 +132,9 @@ class CitationEnv:
     def init_ref(self, **kwargs):
         self.levels, self.starts = self.draw_reference()
         self.theta_trim = np.rad2deg(self.x[7])
-        self.ref = [_RefSignal(self.levels[0], self.starts[0], self.theta_trim),
-                    _RefSignal(self.levels[1], self.starts[1], 0.0), lambda t: 0.0]
+        sw = refsig.widths(self.t_max)[1]
+        self.ref = [_RefSignal(self.levels[0], self.starts[0], self.theta_trim, sw),
+                    _RefSignal(self.levels[1], self.starts[1], 0.0, sw), lambda t: 0.0]
 
     # ---- native plant on the device ----
     def _plant(self, fn, *args):

@@ -52,7 +52,7 @@ TRACE_COLS = 22
 
 
 def population_rollout(weights, shape, ref_levels, ref_starts, env_mode, horizon=HORIZON, trace=False, out=None, action_noise=None,
-                       actions=False):
+                       actions=False, t_max=None, smooth_width=None):
     """weights [pop,P] fp32 cuda; ref_levels/ref_starts [n_envs,2,6] f64 cuda; env_mode [n_envs] int32 cuda."""
     if not weights.is_cuda:
         raise _native.NativeError('population_rollout needs CUDA tensors (no CPU fallback)')
@@ -77,9 +77,13 @@ def population_rollout(weights, shape, ref_levels, ref_starts, env_mode, horizon
         if trace:
             r.trace = torch.full((pop, n_envs, horizon, TRACE_COLS), float('nan'), dtype=torch.float64, device=dev)
     stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-    rc = L.serl_rollout(_ptr(weights), pop, ctypes.byref(shape), _ptr(ref_levels), _ptr(ref_starts), _ptr(env_mode),
-                        n_envs, horizon, _ptr(action_noise), _ptr(r.returns), _ptr(r.steps), _ptr(r.fitness),
-                        _ptr(r.trace), _ptr(getattr(r, 'actions', None)), stream)
+    args = (_ptr(weights), pop, ctypes.byref(shape), _ptr(ref_levels), _ptr(ref_starts), _ptr(env_mode),
+            n_envs, horizon, _ptr(action_noise), _ptr(r.returns), _ptr(r.steps), _ptr(r.fitness),
+            _ptr(r.trace), _ptr(getattr(r, 'actions', None)))
+    if t_max is None:
+        rc = L.serl_rollout(*args, stream)
+    else:      # evaluation mode (envs/phlabenv.py:295-301): longer episodes, wider reference transitions
+        rc = L.serl_rollout_eval(*args, ctypes.c_double(t_max), ctypes.c_double(smooth_width if smooth_width is not None else float(t_max // 6)), stream)
     _native.check(rc, 'serl_rollout')
     return r
 

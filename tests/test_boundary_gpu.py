@@ -149,3 +149,19 @@ def test_smoothness_kernel_matches_reference_formula():
         for e in range(3):
             ref = calc_smoothness(a[i, e, :steps[i, e]])
             assert abs(sm[i, e] - ref) <= 2e-5 * abs(ref) + 1e-9, (i, e, sm[i, e], ref)
+
+
+def test_evaluation_mode_80s_episode_matches_oracle():
+    """set_eval_mode (envs/phlabenv.py:295-301): t_max = 80 s -> 8001 steps, reference widths scaled (block 16 s, smooth 13 s)."""
+    from serl_b200 import rollout
+    from oracle import refsig
+    w = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'actors.npz'))['serl10_elite_h72_tanh'][None]
+    lv, st = refsig.make_ref_params(1, seed_base=80, t_max=80)
+    assert 15.5 < st[0, 0, 1] < 16.5
+    dev = torch.device('cuda:0')
+    md = torch.tensor([rollout.mode_code('nominal')], dtype=torch.int32, device=dev)
+    r = rollout.population_rollout(torch.as_tensor(w, device=dev), rollout.actor_shape(72), torch.as_tensor(lv, device=dev),
+                                   torch.as_tensor(st, device=dev), md, horizon=8001, t_max=80.0, smooth_width=13.0)
+    o = phlab.run_episode(phlab.CitationEnv('nominal', 'auto', t_max=80), OA.unflatten(w[0], hidden=72), lv[0], st[0])
+    assert o['steps'] == 8001 and int(r.steps[0, 0]) == 8001
+    assert abs(float(r.returns[0, 0]) - o['fitness']) <= 1e-4 * abs(o['fitness'])
