@@ -162,6 +162,21 @@ def test_evaluation_mode_80s_episode_matches_oracle():
     md = torch.tensor([rollout.mode_code('nominal')], dtype=torch.int32, device=dev)
     r = rollout.population_rollout(torch.as_tensor(w, device=dev), rollout.actor_shape(72), torch.as_tensor(lv, device=dev),
                                    torch.as_tensor(st, device=dev), md, horizon=8001, t_max=80.0, smooth_width=13.0)
-    o = phlab.run_episode(phlab.CitationEnv('nominal', 'auto', t_max=80), OA.unflatten(w[0], hidden=72), lv[0], st[0])
+    from test_rollout_gpu import _F64Actor
+    env = phlab.CitationEnv('nominal', 'auto', t_max=80)
+    act = OA.unflatten(w[0], hidden=72)
+    o = phlab.run_episode(env, act, lv[0], st[0])
+    o64 = phlab.run_episode(env, _F64Actor(act), lv[0], st[0])
     assert o['steps'] == 8001 and int(r.steps[0, 0]) == 8001
-    assert abs(float(r.returns[0, 0]) - o['fitness']) <= 1e-4 * abs(o['fitness'])
+    # this 80 s flight bifurcates around t = 55 s: the oracle's own float32 vs float64 forward pass differ by 0.5 % in
+    # return; same criterion as tests/test_rollout_gpu.py::check
+    sens = abs(o64['fitness'] - o['fitness']) / abs(o['fitness'])
+    assert abs(float(r.returns[0, 0]) - o['fitness']) <= max(1e-4, 4 * sens) * abs(o['fitness'])
+    # and a well-conditioned prefix: the first 40 s (4001 steps) must agree tightly
+    r40 = rollout.population_rollout(torch.as_tensor(w, device=dev), rollout.actor_shape(72), torch.as_tensor(lv, device=dev),
+                                     torch.as_tensor(st, device=dev), md, horizon=4001, t_max=80.0, smooth_width=13.0)
+    env40 = phlab.CitationEnv('nominal', 'auto', t_max=80)
+    obs = env40.reset(lv[0], st[0]); tot = 0.0
+    for _ in range(4001):
+        obs, rew, done, _ = env40.step(act.select_action(obs)); tot += rew
+    assert int(r40.steps[0, 0]) == 4001 and abs(float(r40.returns[0, 0]) - tot) <= 1e-4 * abs(tot)
