@@ -361,7 +361,17 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu:
             v, steps, cores, wall, kind = cpu_reference_throughput(n_episodes_per_core=3)
-            line['cpu_baseline'] = {'value': v, 'unit': 'env-steps/s', 'cores': cores, 'kind': kind,
+            # a tougher CPU number next to the reference's own execution model: the same path as optimised C + OpenMP
+            # (oracle/fast.py; plant restatement + fp32 forward + wrapper, no Python / torch per-step dispatch)
+            from oracle import fast
+            from serl_b200 import refsig as _rs
+            cw = population(2 * cores)
+            clv, cst = _rs.make_ref_params(8)
+            t0 = time.perf_counter()
+            _, cstp = fast.evaluate_population(cw, HIDDEN, clv, cst, ['nominal'] * 8, threads=cores)
+            c_port = {'value': float(cstp.sum() / (time.perf_counter() - t0)), 'unit': 'env-steps/s', 'cores': cores, 'kind': 'port',
+                      'sample': '%d actors x 8 envs (%d env-steps), C + OpenMP whole-episode port' % (2 * cores, int(cstp.sum()))}
+            line['cpu_baseline'] = {'value': v, 'unit': 'env-steps/s', 'cores': cores, 'kind': kind, 'optimised_c_port': c_port,
                                     'sample': '%d cores x 3 episodes (%d env-steps total, ~20 s of CPU work) of the same workload, one process per core' % (cores, steps)}
         print(json.dumps(line))
     if world > 1:

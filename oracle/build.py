@@ -17,11 +17,12 @@ LIB = os.path.join(HERE, '_build', 'libplant_oracle.so')
 
 def build(force=False):
     src = os.path.join(HERE, 'plant', 'plant_oracle.c')
+    epi = os.path.join(HERE, 'plant', 'episode.c')
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
-    deps = [src, os.path.join(HERE, 'plant', 'plant_support.h')] + \
+    deps = [src, epi, os.path.join(HERE, 'plant', 'plant_support.h')] + \
         [os.path.join(HERE, 'plant', 'gen', f) for f in os.listdir(os.path.join(HERE, 'plant', 'gen'))]
     if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(d) for d in deps):
-        subprocess.check_call(['gcc', '-O2', '-ffp-contract=off', '-fPIC', '-shared', '-o', LIB, src, '-lm'])
+        subprocess.check_call(['gcc', '-O2', '-ffp-contract=off', '-fopenmp', '-fPIC', '-shared', '-o', LIB, src, epi, '-lm'])
     if os.path.isdir(REF_ENVS):
         os.makedirs(os.path.join(HERE, '_ref'), exist_ok=True)
         for v in VARIANTS:
