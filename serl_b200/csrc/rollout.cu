@@ -898,7 +898,16 @@ static int rollout_impl(const float* d_weights, int32_t pop, const serl_actor_sh
     if (warp_ok) {
         // two actors per CTA (8 autonomous warps) when two genomes + the plant tables fit in shared memory; one actor
         // with the tables in shared memory when that fits; else (h = 128) one actor and the tables through L1
-        const bool two = (size_t)PT_TOTAL * sizeof(real) + 2ull * P4 * 4 <= 227 * 1024 && pop > 1;
+        // ... and when that still leaves at least one CTA per SM: a small population spreads over more SMs with one
+        // actor per CTA (4 warps each) instead of filling half as many SMs with 8 warps
+        static int num_sms = 0;
+        if (num_sms == 0) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
+        }
+        const long ctas2 = (long)((pop + 1) / 2) * ((n_envs + ROLLOUT_THREADS - 1) / ROLLOUT_THREADS);
+        const bool two = (size_t)PT_TOTAL * sizeof(real) + 2ull * P4 * 4 <= 227 * 1024 && pop > 1 && ctas2 >= num_sms;
         const bool tabs = (size_t)PT_TOTAL * sizeof(real) + (size_t)P4 * 4 <= 227 * 1024;
         static int apc_exp = -1;          // experiment knob (SERL_ROLLOUT_APC=3|4, h = 32 only): more resident warps per SM
         if (apc_exp < 0) { const char* v = getenv("SERL_ROLLOUT_APC"); apc_exp = v ? atoi(v) : 0; }
