@@ -182,6 +182,7 @@ class Agent:
     def evaluate_population(self):
         """agent.py:229-245 as one fused launch. Returns (pop_fitness f64[pop] numpy, lengths list, device fitness)."""
         n_envs = int(getattr(self.args, 'num_envs', self.args.num_evals))
+        self._count_before, self._gen_before = (self.num_frames, self.num_episodes), self.gen_frames
         draws = [self.env.draw_reference() for _ in range(n_envs)]
         lv = torch.as_tensor(np.stack([d[0] for d in draws]), device=self.device)
         st = torch.as_tensor(np.stack([d[1] for d in draws]), device=self.device)
@@ -204,6 +205,16 @@ class Agent:
             self.num_frames += int(steps[:, -1].sum()) if steps.size else 0
             self.gen_frames += int(steps[:, -1].sum()) if steps.size else 0
             self.num_episodes += hi - lo
+        world, _ = engine.world_info()
+        if world > 1:
+            # frame / episode counters drive the training loop (base/train.py:102); keep them identical on every rank
+            import torch.distributed as dist
+            f0, e0 = self._count_before
+            cnt = torch.tensor([self.num_frames - f0, self.num_episodes - e0, self.gen_frames - self._gen_before],
+                               dtype=torch.int64, device=self.device)
+            dist.all_reduce(cnt)
+            self.num_frames, self.num_episodes = f0 + int(cnt[0]), e0 + int(cnt[1])
+            self.gen_frames = self._gen_before + int(cnt[2])
         return fitness.cpu().numpy(), lengths, fitness
 
     def train(self):
