@@ -46,3 +46,34 @@ def test_two_gpu_generation_equals_single_gpu_bitwise():
         assert np.array_equal(f1, f2)                                    # fitness after the all-gather
         assert e1 == e2
         assert np.array_equal(g1.view(np.uint32), g2.view(np.uint32))    # post-epoch genomes on every rank
+
+
+def _agent_generation(rank, world, port, out):
+    import types
+    import torch.distributed as dist
+    from serl_b200.core import agent as agent_mod
+    from serl_b200.envs import config
+    from serl_b200.parameters import Parameters
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', init_method='tcp://127.0.0.1:%d' % port, rank=rank, world_size=world,
+                            device_id=torch.device('cuda', rank))
+    os.makedirs('/tmp/serl_test_mg%d' % rank, exist_ok=True)
+    os.chdir('/tmp/serl_test_mg%d' % rank)
+    args = Parameters(types.SimpleNamespace(env='PHlab_attitude_nominal', seed=7, pop_size=7, mut_type='normal', test_ea=True))
+    args.state_dim, args.action_dim, args.hidden_size = 7, 3, 16
+    torch.manual_seed(7); np.random.seed(7); random.seed(7)
+    ag = agent_mod.Agent(args, config.select_env('PHlab_attitude_nominal'))
+    stats = ag.train()
+    out[rank] = (ag.num_frames, ag.num_episodes, ag.pop.genomes.cpu().numpy(), stats['best_train_fitness'], stats['elite_index'])
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
+def test_two_rank_agent_train_stays_in_lockstep():
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_agent_generation, args=(2, 29700 + os.getpid() % 2000, out), nprocs=2, join=True)
+    a, b = out[0], out[1]
+    assert a[0] == b[0] and a[1] == b[1]                       # frame / episode counters
+    assert a[3] == b[3] and a[4] == b[4]
+    assert np.array_equal(a[2].view(np.uint32), b[2].view(np.uint32))
