@@ -82,6 +82,36 @@ int serl_rollout_eval(const float* d_weights, int32_t pop, const serl_actor_shap
                       double* d_returns, int32_t* d_steps, double* d_fitness, double* d_trace, float* d_actions,
                       double t_max, double smooth_width, void* stream);
 
+/* The same launch described by a struct, with the optional inputs / outputs the two entry points above do not carry.
+ *   d_env_order  optional [n_envs] int32 permutation: lane slot j flies env d_env_order[j] (the host sorts envs so that
+ *                the 32 lanes of a warp share fault shims / trim; results are still written at the env's own index)
+ *   d_replay     optional [pop, horizon, SERL_REPLAY_COLS] fp32: the transitions of env `replay_env` of every actor, the
+ *                tuple Agent.evaluate stores when store_transition is set (base/core/agent.py:101-112):
+ *                0-6 obs, 7-9 action fed to the env, 10-16 next_obs, 17 reward, 18 done, 19 cost flag (info['cost'],
+ *                envs/phlabenv.py:369-375 -> critical buffer); rows past the episode's length are not written
+ *   d_status     optional int32 word the kernel ORs error bits into (SERL_STATUS_*); the caller zeroes it and reads it
+ *                after synchronising
+ * t_max <= 0 selects the training defaults (20 s, smooth width 3 s). */
+#define SERL_REPLAY_COLS 20
+enum { SERL_STATUS_NONFINITE = 1 };   /* a trajectory's state / return became NaN or infinite */
+typedef struct {
+    const float* d_weights; int32_t pop; serl_actor_shape shape;
+    const double* d_ref_levels; const double* d_ref_starts; const int32_t* d_env_mode; int32_t n_envs; int32_t horizon;
+    const float* d_action_noise;
+    double* d_returns; int32_t* d_steps; double* d_fitness; double* d_trace; float* d_actions;
+    double t_max; double smooth_width;
+    const int32_t* d_env_order;
+    float* d_replay; int32_t replay_env;
+    int32_t* d_status;
+} serl_rollout_desc;
+int serl_rollout_run(const serl_rollout_desc* desc, void* stream);
+
+/* Actor.forward / select_action for a batch (base/core/genetic_agent.py:104-109): d_obs [n, state_dim] fp32 ->
+ * d_actions [n, action_dim] fp32 with ONE genome d_genome [P]; the arithmetic (summation order, activations) is the
+ * rollout kernel's, bit for bit. */
+int serl_actor_forward(const float* d_genome, const serl_actor_shape* shape, const float* d_obs, int32_t n,
+                       float* d_actions, void* stream);
+
 /* K6: action smoothness of n_traj trajectories (base/core/utils.py:82-120 calc_smoothness; agent.py:128-134):
  * out[t] = -sqrt(sum_i sum_k f_k |FFT(y_i)[k]|^2 dt 2/N) * 100 * 80/(N dt) over the N = d_steps[t] executed steps of
  * d_actions [n_traj, horizon, 3]. */

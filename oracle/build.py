@@ -1,6 +1,7 @@
 """Build the oracle's native pieces (checker only).
 
-  oracle/_build/libplant_oracle.so   gcc build of the C restatement oracle/plant/plant_oracle.c
+  oracle/_build/libplant_oracle.so   gcc build of the C restatement oracle/plant/plant_oracle.c, the episode port
+                                     (episode.c) and the kernel-order actor (actor_kernel_order.c)
   oracle/_ref/citation_<variant>.so  byte copies of the reference's own plant binaries (only when
                                      /root/reference exists, i.e. in the build container; the GPU box uses the
                                      copies that travelled with the snapshot)
@@ -18,11 +19,12 @@ LIB = os.path.join(HERE, '_build', 'libplant_oracle.so')
 def build(force=False):
     src = os.path.join(HERE, 'plant', 'plant_oracle.c')
     epi = os.path.join(HERE, 'plant', 'episode.c')
+    ako = os.path.join(HERE, 'plant', 'actor_kernel_order.c')
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
-    deps = [src, epi, os.path.join(HERE, 'plant', 'plant_support.h')] + \
+    deps = [src, epi, ako, os.path.join(HERE, 'plant', 'plant_support.h')] + \
         [os.path.join(HERE, 'plant', 'gen', f) for f in os.listdir(os.path.join(HERE, 'plant', 'gen'))]
     if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(d) for d in deps):
-        subprocess.check_call(['gcc', '-O2', '-ffp-contract=off', '-fopenmp', '-fPIC', '-shared', '-o', LIB, src, epi, '-lm'])
+        subprocess.check_call(['gcc', '-O2', '-ffp-contract=off', '-fopenmp', '-fPIC', '-shared', '-o', LIB, src, epi, ako, '-lm'])
     if os.path.isdir(REF_ENVS):
         os.makedirs(os.path.join(HERE, '_ref'), exist_ok=True)
         for v in VARIANTS:

@@ -17,8 +17,10 @@ def mode_code(mode):
 
 
 def evaluate_population(genomes, hidden, levels, starts, modes, num_layers=3, activation='tanh', t_max=20.0, smooth_w=3.0,
-                        horizon=2001, threads=None):
-    """genomes [pop,P] f32; levels/starts [n_envs,2,6]; modes list of env mode strings -> (returns [pop,n_envs], steps)."""
+                        horizon=2001, threads=None, actor_order='index'):
+    """genomes [pop,P] f32; levels/starts [n_envs,2,6]; modes list of env mode strings -> (returns [pop,n_envs], steps).
+    actor_order: 'index' (plain index-order sums + libm tanh: a stand-in for the reference's torch forward pass) or
+    'kernel' (the device kernel's summation order and activation arithmetic, oracle/plant/actor_kernel_order.c)."""
     if threads:
         os.environ['OMP_NUM_THREADS'] = str(int(threads))
     lib = ctypes.CDLL(_build.build())
@@ -32,5 +34,33 @@ def evaluate_population(genomes, hidden, levels, starts, modes, num_layers=3, ac
     stp = np.zeros((pop, n_envs), dtype=np.int32)
     vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
     lib.oracle_population(vp(g), pop, g.shape[1], 7, 3, int(hidden), int(num_layers), _ACT[activation], vp(md), vp(lv), vp(st), n_envs,
-                          ctypes.c_double(t_max), ctypes.c_double(smooth_w), int(horizon), vp(ret), vp(stp))
+                          ctypes.c_double(t_max), ctypes.c_double(smooth_w), int(horizon), vp(ret), vp(stp),
+                          {'index': 0, 'kernel': 1}[actor_order])
     return ret, stp
+
+
+def actor_forward_kernel_order(genome, obs, hidden, num_layers=3, activation='tanh'):
+    """the kernel-order actor on a batch of observations [n,7] -> actions [n,3] (float32, bit-exact with the GPU)."""
+    lib = ctypes.CDLL(_build.build())
+    g = np.ascontiguousarray(genome, dtype=np.float32)
+    o = np.ascontiguousarray(obs, dtype=np.float32)
+    out = np.empty((o.shape[0], 3), dtype=np.float32)
+    vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    lib.ko_actor_forward_batch(vp(g), 7, 3, int(hidden), int(num_layers), _ACT[activation], vp(o), o.shape[0], vp(out))
+    return out
+
+
+def tanh_kernel_order(x):
+    lib = ctypes.CDLL(_build.build())
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    y = np.empty_like(x)
+    lib.ko_tanhf_batch(x.ctypes.data_as(ctypes.c_void_p), x.size, y.ctypes.data_as(ctypes.c_void_p))
+    return y
+
+
+def expm1_neg_kernel_order(x):
+    lib = ctypes.CDLL(_build.build())
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    y = np.empty_like(x)
+    lib.ko_expm1f_neg_batch(x.ctypes.data_as(ctypes.c_void_p), x.size, y.ctypes.data_as(ctypes.c_void_p))
+    return y

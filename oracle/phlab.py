@@ -55,7 +55,7 @@ class CitationEnv:
         return self.obs
 
     def ref_deg(self):
-        return np.array([refsig.ref_value_deg(self.levels[0], self.starts[0], self.t, self.theta_trim, self.smooth_w),
+        return np.array([refsig.ref_value_deg(self.levels[0], self.starts[0], self.t, self.theta_trim, self.smooth_w, self.t_max),
                          refsig.ref_value_deg(self.levels[1], self.starts[1], self.t, 0.0, self.smooth_w), 0.0])
 
     # phlabenv.py:430-482

@@ -71,9 +71,14 @@ static void apply_fault(int fault, const double* u, double* c)
     else if (fault == 4) { const double b = 2.5 * DEG2RAD; c[0] = fmin(fmax(u[0], -b), b); }
 }
 
-/* one episode; mode = variant | fault << 8; levels / starts: [2][6]; returns the episodic return, *steps = executed steps */
+void ko_actor_forward(const float* p, int S, int A, int H, int L, int act, const float* obs, float* action);   /* actor_kernel_order.c */
+
+/* one episode; mode = variant | fault << 8; levels / starts: [2][6]; returns the episodic return, *steps = executed steps.
+ * actor_order: 0 = index-order float32 sums + libm tanh (a stand-in for the reference's torch forward), 1 = the device
+ * kernel's summation order and activation arithmetic (actor_kernel_order.c): the GPU must reproduce mode 1 exactly. */
 double oracle_episode(const float* genome, int S, int A, int H, int L, int act, int mode,
-                      const double* levels, const double* starts, double t_max, double smooth_w, int horizon, int* steps)
+                      const double* levels, const double* starts, double t_max, double smooth_w, int horizon, int* steps,
+                      int actor_order)
 {
     const double DEG2RAD = 0.017453292519943295, RAD2DEG = 57.29577951308232;
     const double bound = 10.0 * DEG2RAD, max_theta = 60.0 * DEG2RAD, max_phi = 75.0 * DEG2RAD;
@@ -89,7 +94,8 @@ double oracle_episode(const float* genome, int S, int A, int H, int L, int act, 
     int k = 0;
     for (; k < horizon;) {
         float a[3];
-        actor_forward(genome, S, A, H, L, act, obs, a);
+        if (actor_order == 1) ko_actor_forward(genome, S, A, H, L, act, obs, a);
+        else actor_forward(genome, S, A, H, L, act, obs, a);
         for (int i = 0; i < 3; ++i) {
             const float t1 = a[i] + 1.0f;
             const float t2 = 0.5f * t1;
@@ -98,7 +104,7 @@ double oracle_episode(const float* genome, int S, int A, int H, int L, int act, 
         apply_fault(fault, U, cmd);
         memcpy(xo, X, sizeof(xo));
         plant_step(variant, X, cmd);
-        const double e0 = ref_deg(levels, starts, t, theta_trim, smooth_w) * DEG2RAD - xo[7];
+        const double e0 = ref_deg(levels, starts, t, t <= t_max ? theta_trim : 0.0, smooth_w) * DEG2RAD - xo[7];   /* Const(0, t_max, trim) */
         const double e1 = ref_deg(levels + 6, starts + 6, t, 0.0, smooth_w) * DEG2RAD - xo[6];
         const double e2 = 0.0 - xo[5];
         const double c0 = fabs(fmin(fmax(k_err * e0, -1.0), 1.0)), c1 = fabs(fmin(fmax(k_err * e1, -1.0), 1.0));
@@ -120,14 +126,14 @@ double oracle_episode(const float* genome, int S, int A, int H, int L, int act, 
 /* pop x n_envs episodes, OpenMP over trajectories; returns total executed steps */
 long oracle_population(const float* genomes, int pop, int P, int S, int A, int H, int L, int act, const int* modes,
                        const double* levels, const double* starts, int n_envs, double t_max, double smooth_w, int horizon,
-                       double* returns, int* steps)
+                       double* returns, int* steps, int actor_order)
 {
     long total = 0;
 #pragma omp parallel for schedule(dynamic, 1) reduction(+ : total)
     for (int j = 0; j < pop * n_envs; ++j) {
         const int a = j / n_envs, e = j % n_envs;
         returns[j] = oracle_episode(genomes + (long)a * P, S, A, H, L, act, modes[e], levels + (long)e * 12, starts + (long)e * 12,
-                                    t_max, smooth_w, horizon, steps + j);
+                                    t_max, smooth_w, horizon, steps + j, actor_order);
         total += steps[j];
     }
     return total;

@@ -13,6 +13,20 @@ class ActorShape(ctypes.Structure):
                 ('num_layers', ctypes.c_int32), ('activation', ctypes.c_int32)]
 
 
+class RolloutDesc(ctypes.Structure):
+    """serl_rollout_desc (include/serl_b200.h)"""
+    _fields_ = [('d_weights', ctypes.c_void_p), ('pop', ctypes.c_int32), ('shape', ActorShape),
+                ('d_ref_levels', ctypes.c_void_p), ('d_ref_starts', ctypes.c_void_p), ('d_env_mode', ctypes.c_void_p),
+                ('n_envs', ctypes.c_int32), ('horizon', ctypes.c_int32), ('d_action_noise', ctypes.c_void_p),
+                ('d_returns', ctypes.c_void_p), ('d_steps', ctypes.c_void_p), ('d_fitness', ctypes.c_void_p),
+                ('d_trace', ctypes.c_void_p), ('d_actions', ctypes.c_void_p),
+                ('t_max', ctypes.c_double), ('smooth_width', ctypes.c_double),
+                ('d_env_order', ctypes.c_void_p), ('d_replay', ctypes.c_void_p), ('replay_env', ctypes.c_int32),
+                ('d_status', ctypes.c_void_p)]
+
+
+REPLAY_COLS = 20
+STATUS_NONFINITE = 1
 ACTIVATIONS = {'tanh': 0, 'elu': 1, 'relu': 2}
 _lib = None
 
@@ -35,6 +49,10 @@ def lib():
         L.serl_rollout.argtypes = [vp, i32, ctypes.POINTER(ActorShape), vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp]
         L.serl_rollout_eval.restype = ctypes.c_int
         L.serl_rollout_eval.argtypes = L.serl_rollout.argtypes[:-1] + [ctypes.c_double, ctypes.c_double, vp]
+        L.serl_rollout_run.restype = ctypes.c_int
+        L.serl_rollout_run.argtypes = [ctypes.POINTER(RolloutDesc), vp]
+        L.serl_actor_forward.restype = ctypes.c_int
+        L.serl_actor_forward.argtypes = [vp, ctypes.POINTER(ActorShape), vp, i32, vp, vp]
         L.serl_smoothness.restype = ctypes.c_int
         L.serl_smoothness.argtypes = [vp, vp, i32, i32, ctypes.c_double, vp, vp]
         L.serl_launch_count.restype = i64

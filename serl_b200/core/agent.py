@@ -123,7 +123,7 @@ class Agent:
         theta_trim = np.rad2deg(x_ic[7])
         from ..envs.phlabenv import _RefSignal
         sw = refsig.widths(env.t_max)[1]
-        refs = [_RefSignal(levels[0], starts[0], theta_trim, sw), _RefSignal(levels[1], starts[1], 0.0, sw), lambda t: 0.0]
+        refs = [_RefSignal(levels[0], starts[0], theta_trim, sw, env.t_max), _RefSignal(levels[1], starts[1], 0.0, sw), lambda t: 0.0]
         return self._episode_from_trace(agent, tr, n, x_ic, store_transition, refs)
 
     _ic_cache: Dict[int, np.ndarray] = {}

@@ -23,6 +23,7 @@
 
 #include "../../include/serl_b200.h"
 #include "common.cuh"
+#include "actor_math.cuh"
 
 #ifdef PLANT_F32
 typedef float real;      // experimental build: single-precision right-hand side, double-precision integrator state
@@ -138,21 +139,22 @@ __device__ __forceinline__ double plant_cos_fast(double x) { double s, c; plant_
 #define PLANT_IC_TABLE static __device__ const double plant_ic_table[SERL_PLANT_COUNT][19]
 #define PLANT_PV_TABLE static __device__ const real plant_pv[SERL_PLANT_COUNT][PLANT_NPV]
 #define PLANT_PV(k) plant_pvrow[k]
+// the right-hand side works on the 14 live continuous states only: rtX index -> position in the compact arrays
+#define PLANT_XI(i) ((i) < 8 ? (i) : ((i) == 9 ? 8 : ((i) == 12 ? 9 : (i) - 5)))
 #include PLANT_GEN(plant_ic.h)
-#include PLANT_GEN(plant_rhs_common.h)     // h2000_v90, cg, cg_for, h2000_v150, h10000_v90: one function + parameter rows
-#include PLANT_GEN(plant_rhs_ice.h)        // structurally different build
+#include PLANT_GEN(plant_rhs_common.h)     // ONE function for every plant variant + per-variant parameter rows
+#undef PLANT_XI
+#define PLANT_XI(i) (i)                    // trace-only navigation states: full rtX indexing
 #include PLANT_GEN(plant_rhs_nav.h)
 
-#define ROLLOUT_THREADS 128
+
 #define NX 19
+#define NLIVE 14
+#define MAX_CTA_THREADS 256
 
 // live continuous states of the plant: p q r V alpha beta phi theta | h | washout | N1 N1 N2 N2
 // (psi, x_e, y_e never feed back and are integrated only for traces; Parameter_CSTATE(_g) are folded constants).
-__device__ __forceinline__ void plant_rhs(int variant, const real* X, const real* U, real* xdot, const real* tab)
-{
-    if (variant == SERL_PLANT_ICE) plant_rhs_ice(X, U, xdot, tab);
-    else plant_rhs_common(X, U, xdot, tab, plant_pv[variant]);
-}
+// `pv` = this variant's parameter row (shared memory copy of plant_pv, or the global table).
 
 __device__ __forceinline__ const double* plant_ic(int variant) { return plant_ic_table[variant]; }
 
@@ -167,11 +169,11 @@ __device__ __forceinline__ const double* plant_ic(int variant) { return plant_ic
         {35.0 / 384.0, 0, 500.0 / 1113.0, 125.0 / 192.0, -2187.0 / 6784.0, 11.0 / 84.0}}
 #define ODE5_LIVE_INIT {0, 1, 2, 3, 4, 5, 6, 7, 9, 12, 15, 16, 17, 18}
 static __constant__ double c_ode5_B[6][6] = ODE5_B_INIT;      // dynamically indexed copy (trace path)
-static __constant__ int c_ode5_live[14] = ODE5_LIVE_INIT;
+static __constant__ int c_ode5_live[NLIVE] = ODE5_LIVE_INIT;
 
 // trace mode only: psi, x_e, y_e (rtX 8, 10, 11).  Their derivatives depend on the live states alone, so they are
-// integrated after the fact with the same stage states, rebuilt from the stored stage derivatives f[6][NX].
-__device__ __noinline__ void plant_step_nav(double* Xnav, const double* X0, const real (*f)[NX], const real* U, const real* tab)
+// integrated after the fact with the same stage states, rebuilt from the stored stage derivatives f[6][NLIVE].
+__device__ __noinline__ void plant_step_nav(double* Xnav, const double* X0, const real (*f)[NLIVE], const real* U, const real* tab)
 {
     const double h = 0.01;
     const int NAV[3] = {8, 10, 11};
@@ -181,10 +183,10 @@ __device__ __noinline__ void plant_step_nav(double* Xnav, const double* X0, cons
     for (int s = 0; s < 6; ++s) {
         for (int i = 0; i < NX; ++i) xs[i] = X0[i];
         if (s > 0) {
-            for (int li = 0; li < 14; ++li) {
+            for (int li = 0; li < NLIVE; ++li) {
                 const int i = c_ode5_live[li];
-                double acc = (double)f[0][i] * (h * c_ode5_B[s - 1][0]);
-                for (int j = 1; j < s; ++j) acc += (double)f[j][i] * (h * c_ode5_B[s - 1][j]);
+                double acc = (double)f[0][li] * (h * c_ode5_B[s - 1][0]);
+                for (int j = 1; j < s; ++j) acc += (double)f[j][li] * (h * c_ode5_B[s - 1][j]);
                 xs[i] = X0[i] + acc;
             }
             for (int q = 0; q < 3; ++q) {
@@ -204,32 +206,30 @@ __device__ __noinline__ void plant_step_nav(double* Xnav, const double* X0, cons
     }
 }
 
-// Stage loop fully unrolled (every f[j][i] load of a stage is independent, h*B folds to constants); the right-hand
-// sides are __noinline__ calls, so x and the stage derivatives f live in local memory (L1/L2-resident scratch: it is
-// the source of the kernel's DRAM write-back traffic, see profiles/).  A rolled loop with the RHS inlined cuts that
-// traffic 20x but runs 22 % slower (measured), so this form is kept.  The integrator state and the stage
+// Stage loop fully unrolled (every f[j][li] load of a stage is independent, h*B folds to constants).  The right-hand side
+// is ONE __noinline__ function (the same code for every plant variant), so the compact state x[14] and the stage
+// derivatives f[6][14] live in local memory (896 B per thread, L1-resident).  The integrator state and the stage
 // combinations are double in every build; `real` (the type of the right-hand side) is double unless PLANT_F32.
-__device__ void plant_step(int variant, double* X, const double* U, const real* tab, bool nav = false)
+__device__ __noinline__ void plant_step(const real* pv, double* X, const double* U, const real* tab, bool nav = false)
 {
     constexpr double h = 0.01;
     constexpr double B[6][6] = ODE5_B_INIT;
-    constexpr int LIVE[14] = ODE5_LIVE_INIT;
-    real f[6][NX], x[NX], u[3];
+    constexpr int LIVE[NLIVE] = ODE5_LIVE_INIT;
+    real f[6][NLIVE], x[NLIVE], u[3];
     u[0] = (real)U[0]; u[1] = (real)U[1]; u[2] = (real)U[2];
 #pragma unroll
-    for (int i = 0; i < NX; ++i) x[i] = (real)X[i];
-    double xl[14];
+    for (int li = 0; li < NLIVE; ++li) x[li] = (real)X[LIVE[li]];
+    double xl[NLIVE];
 #pragma unroll
     for (int s = 0; s < 6; ++s) {
-        plant_rhs(variant, x, u, f[s], tab);
+        plant_rhs_common(x, u, f[s], tab, pv);
 #pragma unroll
-        for (int li = 0; li < 14; ++li) {
-            const int i = LIVE[li];
-            double acc = (double)f[0][i] * (h * B[s][0]);
+        for (int li = 0; li < NLIVE; ++li) {
+            double acc = (double)f[0][li] * (h * B[s][0]);
 #pragma unroll
-            for (int j = 1; j <= s; ++j) acc += (double)f[j][i] * (h * B[s][j]);
-            xl[li] = X[i] + acc;
-            x[i] = (real)xl[li];
+            for (int j = 1; j <= s; ++j) acc += (double)f[j][li] * (h * B[s][j]);
+            xl[li] = X[LIVE[li]] + acc;
+            x[li] = (real)xl[li];
         }
     }
     if (nav) {
@@ -238,15 +238,11 @@ __device__ void plant_step(int variant, double* X, const double* U, const real* 
         X[8] = xn[0]; X[10] = xn[1]; X[11] = xn[2];
     }
 #pragma unroll
-    for (int li = 0; li < 14; ++li) X[LIVE[li]] = xl[li];
+    for (int li = 0; li < NLIVE; ++li) X[LIVE[li]] = xl[li];
 }
 
-__device__ __forceinline__ float act_fn(int act, float x)
-{
-    if (act == SERL_ACT_TANH) return tanhf(x);
-    if (act == SERL_ACT_ELU) return x > 0.f ? x : expm1f(x);
-    return x > 0.f ? x : 0.01f * x;
-}
+// activations: IEEE-only sequences of actor_math.cuh (bit-reproducible on a CPU; see oracle/plant/actor_kernel_order.c)
+__device__ __forceinline__ float act_fn(int act, float x) { return am_act1(act, x); }
 
 // reference-signal value in degrees (serl_b200/refsig.py; recovered shape of signals.RandomizedCosineStepSequence)
 __device__ __forceinline__ double ref_deg(const double* __restrict__ lv, const double* __restrict__ st, double t, double offset, double smooth_w)
@@ -262,6 +258,17 @@ __device__ __forceinline__ double ref_deg(const double* __restrict__ lv, const d
 }
 
 // ---- per-trajectory environment (CitationEnv restated for one thread) --------------------------------------
+// hand-over record of a trajectory that is continued by another CTA slot (time-split schedule, see rollout_kernel_persist)
+struct Handoff {
+    double* X;      // [NX][n]
+    double* t;      // [n]
+    double* ret;    // [n]
+    float* obs;     // [7][n]
+    int* k;         // [n]  executed steps | done << 30
+    int* flag;      // [n / 32] one word per warp, 1 when the record is complete
+    long long n;
+};
+
 struct RolloutArgs {
     const float* weights; int P; serl_actor_shape sh;
     const double* ref_levels; const double* ref_starts; const int* env_mode; int n_envs; int horizon;
@@ -271,15 +278,27 @@ struct RolloutArgs {
     int pop;
     double t_max;                   // episode length [s] (envs/phlabenv.py:181; 80 in evaluation mode :295-301)
     double smooth_w;                // width of the raised-cosine reference transitions [s] (t_max // 6)
+    const int* env_order;           // optional [n_envs]: lane slot -> env index
+    float* replay; int replay_env;  // optional [pop, horizon, SERL_REPLAY_COLS] transitions of one env per actor
+    int* status;                    // optional device status word
+    // persistent schedule
+    const float* wt;                // [pop][P4] genomes in the shared-memory layout (transposed matrices), 16-byte aligned rows
+    int P4;                         // row stride of wt / smem slot size in floats (multiple of 4)
+    int apc, wps;                   // genome slots per CTA, warps per slot
+    int n_chunks;                   // env chunks of wps*32 lanes per actor
+    long long n_tasks;              // pop * n_chunks
+    long long n_slots;              // gridDim.x * apc
+    Handoff ho;
 };
 
 struct Env {
     double X[NX];
     const real* tab;         // plant tables (shared or global memory)
+    const real* pv;          // parameter row of this env's plant variant
     const double* ref_lv;    // this env's reference-signal levels / starts [2][SERL_REF_BLOCKS] (global, read per step)
     const double* ref_st;
     double t, ret, theta_trim;
-    int variant, fault, k;
+    int fault, k;
     bool done;
 };
 
@@ -295,28 +314,34 @@ __device__ __forceinline__ void apply_fault(int fault, const double* u, double* 
     else if (fault == SERL_FAULT_SE) { const double b = 2.5 * DEG2RAD; c[0] = fmin(fmax(u[0], -b), b); }   // envs/se :73-79
 }
 
-// reset(): initialize(), one zero-command step returns the initial state (phlabenv.py:401-428). obs = [0,0,0,p,q,r,alpha]
-__device__ void env_reset(Env& e, const RolloutArgs& a, int env, float* obs)
+// bind the env's constants (plant variant row, fault shim, reference signals, trim pitch); no dynamics
+__device__ __forceinline__ void env_bind(Env& e, const RolloutArgs& a, int env, const real* pv_base)
 {
     const int mode = a.env_mode[env];
-    e.variant = mode & 0xff;
+    const int variant = mode & 0xff;
+    e.pv = pv_base + variant * PLANT_NPV;
     e.fault = (mode >> 8) & 0xff;
     e.ref_lv = a.ref_levels + (size_t)env * 2 * SERL_REF_BLOCKS;
     e.ref_st = a.ref_starts + (size_t)env * 2 * SERL_REF_BLOCKS;
-    const double* ic = plant_ic(e.variant);
+    e.theta_trim = plant_ic(variant)[7] * RAD2DEG;
+}
+
+// reset(): initialize(), one zero-command step returns the initial state (phlabenv.py:401-428). obs = [0,0,0,p,q,r,alpha]
+__device__ void env_reset(Env& e, const RolloutArgs& a, int env, float* obs)
+{
+    const double* ic = plant_ic(a.env_mode[env] & 0xff);
 #pragma unroll
     for (int i = 0; i < NX; ++i) e.X[i] = ic[i];
     obs[0] = obs[1] = obs[2] = 0.f;
     obs[3] = (float)e.X[0]; obs[4] = (float)e.X[1]; obs[5] = (float)e.X[2]; obs[6] = (float)e.X[4];
-    e.theta_trim = e.X[7] * RAD2DEG;
     double U[3] = {0.0, 0.0, 0.0}, cmd[3];
     apply_fault(e.fault, U, cmd);
-    plant_step(e.variant, e.X, cmd, e.tab, a.trace != nullptr);
+    plant_step(e.pv, e.X, cmd, e.tab, a.trace != nullptr);
     e.t = 0.0; e.ret = 0.0; e.k = 0; e.done = false;
 }
 
 // one CitationEnv.step (phlabenv.py:430-482) + the bookkeeping of Agent.evaluate (agent.py:85-118)
-__device__ void env_step(Env& e, const RolloutArgs& ar, size_t traj, const float* a, float* obs)
+__device__ void env_step(Env& e, const RolloutArgs& ar, size_t traj, int actor, bool replay, const float* a, float* obs)
 {
     const double bound = 10.0 * DEG2RAD;                       // phlabenv.py:208
     const double max_theta = 60.0 * DEG2RAD, max_phi = 75.0 * DEG2RAD;
@@ -336,8 +361,8 @@ __device__ void env_step(Env& e, const RolloutArgs& ar, size_t traj, const float
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
             act_d[i] = (double)a[i];
-            const float t1 = a[i] + 1.0f;
-            const float t2 = 0.5f * t1;
+            const float t1 = __fadd_rn(a[i], 1.0f);
+            const float t2 = __fmul_rn(0.5f, t1);
             U[i] = -bound + (double)t2 * (bound - (-bound));
         }
     }
@@ -345,10 +370,11 @@ __device__ void env_step(Env& e, const RolloutArgs& ar, size_t traj, const float
     double xo[12];
 #pragma unroll
     for (int i = 0; i < 12; ++i) xo[i] = e.X[i];
-    plant_step(e.variant, e.X, cmd, e.tab, ar.trace != nullptr);
+    plant_step(e.pv, e.X, cmd, e.tab, ar.trace != nullptr);
 
     const double t = e.t;
-    const double r_th = ref_deg(e.ref_lv, e.ref_st, t, e.theta_trim, ar.smooth_w) * DEG2RAD;
+    // + signals.Const(0., t_max, theta_trim) (phlabenv.py:344): the trim offset exists on [0, t_max] only
+    const double r_th = ref_deg(e.ref_lv, e.ref_st, t, t <= ar.t_max ? e.theta_trim : 0.0, ar.smooth_w) * DEG2RAD;
     const double r_ph = ref_deg(e.ref_lv + SERL_REF_BLOCKS, e.ref_st + SERL_REF_BLOCKS, t, 0.0, ar.smooth_w) * DEG2RAD;
     const double e0 = r_th - xo[7], e1 = r_ph - xo[6], e2 = 0.0 - xo[5];
     const double c0 = fabs(fmin(fmax(k_err * e0, -1.0), 1.0));
@@ -371,23 +397,40 @@ __device__ void env_step(Env& e, const RolloutArgs& ar, size_t traj, const float
         tr[16] = act_d[0]; tr[17] = act_d[1]; tr[18] = act_d[2];
         tr[19] = e0; tr[20] = e1; tr[21] = e2;
     }
-    obs[0] = (float)e0; obs[1] = (float)e1; obs[2] = (float)e2;
-    obs[3] = (float)xo[0]; obs[4] = (float)xo[1]; obs[5] = (float)xo[2]; obs[6] = (float)xo[4];
+    const float o0 = (float)e0, o1 = (float)e1, o2 = (float)e2;
+    const float o3 = (float)xo[0], o4 = (float)xo[1], o5 = (float)xo[2], o6 = (float)xo[4];
+    if (replay) {
+        // the transition Agent.evaluate stores (agent.py:101-112) + the cost flag of get_cost (phlabenv.py:369-375,
+        // including its degrees-vs-radians comparison on the bank angle)
+        float* rp = ar.replay + ((size_t)actor * ar.horizon + e.k) * SERL_REPLAY_COLS;
+#pragma unroll
+        for (int i = 0; i < 7; ++i) rp[i] = obs[i];
+        rp[7] = (float)act_d[0]; rp[8] = (float)act_d[1]; rp[9] = (float)act_d[2];
+        rp[10] = o0; rp[11] = o1; rp[12] = o2; rp[13] = o3; rp[14] = o4; rp[15] = o5; rp[16] = o6;
+        rp[17] = (float)reward;
+        rp[18] = done ? 1.f : 0.f;
+        const double v0 = plant_ic(ar.env_mode[ar.replay_env] & 0xff)[3];
+        const bool cost = (fabs(xo[4]) * RAD2DEG > 11.0) || (fabs(xo[6]) * RAD2DEG > 0.75 * max_phi) || (xo[3] < v0 / 3.0);
+        rp[19] = cost ? 1.f : 0.f;
+    }
+    obs[0] = o0; obs[1] = o1; obs[2] = o2; obs[3] = o3; obs[4] = o4; obs[5] = o5; obs[6] = o6;
     e.t = t + 0.01;
     e.k += 1;
     e.done = done || (e.k >= ar.horizon);
 }
-
 // ---- simple actor: every thread evaluates the whole MLP for its own observation -------------------------
 __device__ void actor_forward_simple(const float* __restrict__ w, const serl_actor_shape sh, float* bufA, float* bufB,
                                      int tid, int nthr, const float* obs, float* action)
 {
+    // same arithmetic specification as actor_forward_warp (dot products: sequential fma from 0; LayerNorm / output-layer
+    // sums: four contiguous quarter blocks, combined (q0+q1)+(q2+q3)), so both kernels produce identical bits
     const int S = sh.state_dim, A = sh.action_dim, H = sh.hidden, L = sh.num_layers;
+    const int TM = (H + 3) / 4;
     const float* p = w;
     for (int j = 0; j < H; ++j) {
         float acc = 0.f;
-        for (int i = 0; i < S; ++i) acc = fmaf(p[j * S + i], obs[i], acc);
-        acc += p[H * S + j];
+        for (int i = 0; i < S; ++i) acc = __fmaf_rn(p[j * S + i], obs[i], acc);
+        acc = __fadd_rn(acc, p[H * S + j]);
         bufA[j * nthr + tid] = act_fn(sh.activation, acc);
     }
     p += H * S + H;
@@ -398,61 +441,44 @@ __device__ void actor_forward_simple(const float* __restrict__ w, const serl_act
         const float* b = p + H * H;
         const float* gamma = b + H;
         const float* beta = gamma + H;
-        float sum = 0.f;
-        for (int j = 0; j < H; ++j) {
-            float acc = 0.f;
-            for (int i = 0; i < H; ++i) acc = fmaf(W[j * H + i], in[i * nthr + tid], acc);
-            acc += b[j];
-            out[j * nthr + tid] = acc;
-            sum += acc;
+        float q[4];
+        for (int g = 0; g < 4; ++g) {
+            float sum = 0.f;
+            for (int j = g * TM; j < min((g + 1) * TM, H); ++j) {
+                float acc = 0.f;
+                for (int i = 0; i < H; ++i) acc = __fmaf_rn(W[j * H + i], in[i * nthr + tid], acc);
+                acc = __fadd_rn(acc, b[j]);
+                out[j * nthr + tid] = acc;
+                sum = __fadd_rn(sum, acc);
+            }
+            q[g] = sum;
         }
-        const float mean = sum / (float)H;
-        float ss = 0.f;
-        for (int j = 0; j < H; ++j) {
-            const float d = out[j * nthr + tid] - mean;
-            ss = fmaf(d, d, ss);
+        const float mean = __fdiv_rn(__fadd_rn(__fadd_rn(q[0], q[1]), __fadd_rn(q[2], q[3])), (float)H);
+        for (int g = 0; g < 4; ++g) {
+            float ss = 0.f;
+            for (int j = g * TM; j < min((g + 1) * TM, H); ++j) {
+                const float d = __fadd_rn(out[j * nthr + tid], -mean);
+                out[j * nthr + tid] = d;
+                ss = __fmaf_rn(d, d, ss);
+            }
+            q[g] = ss;
         }
-        const float den = sqrtf(ss / (float)(H - 1)) + 1e-6f;
-        for (int j = 0; j < H; ++j) {
-            const float d = out[j * nthr + tid] - mean;
-            out[j * nthr + tid] = act_fn(sh.activation, gamma[j] * d / den + beta[j]);
-        }
+        const float var = __fdiv_rn(__fadd_rn(__fadd_rn(q[0], q[1]), __fadd_rn(q[2], q[3])), (float)(H - 1));
+        const float inv = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(var), 1e-6f));
+        for (int j = 0; j < H; ++j)
+            out[j * nthr + tid] = act_fn(sh.activation, __fmaf_rn(__fmul_rn(gamma[j], out[j * nthr + tid]), inv, beta[j]));
         p += H * H + 3 * H;
         float* t = in; in = out; out = t;
     }
     for (int j = 0; j < A; ++j) {
-        float acc = 0.f;
-        for (int i = 0; i < H; ++i) acc = fmaf(p[j * H + i], in[i * nthr + tid], acc);
-        acc += p[A * H + j];
-        action[j] = tanhf(acc);
+        float q[4];
+        for (int g = 0; g < 4; ++g) {
+            float acc = 0.f;
+            for (int i = g * TM; i < min((g + 1) * TM, H); ++i) acc = __fmaf_rn(p[j * H + i], in[i * nthr + tid], acc);
+            q[g] = acc;
+        }
+        action[j] = am_tanh1(__fadd_rn(__fadd_rn(__fadd_rn(q[0], q[1]), __fadd_rn(q[2], q[3])), p[A * H + j]));
     }
-}
-
-__global__ void __launch_bounds__(ROLLOUT_THREADS)
-rollout_kernel_simple(RolloutArgs ar)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* w = reinterpret_cast<float*>(smem_raw);
-    const int P4 = (ar.P + 3) & ~3;
-    float* bufA = w + P4;
-    float* bufB = bufA + ar.sh.hidden * ROLLOUT_THREADS;
-    const int actor = blockIdx.y, tid = threadIdx.x;
-    const int env = blockIdx.x * ROLLOUT_THREADS + tid;
-    const float* gw = ar.weights + (size_t)actor * ar.P;
-    for (int i = tid; i < ar.P; i += ROLLOUT_THREADS) w[i] = gw[i];
-    __syncthreads();
-    if (env >= ar.n_envs) return;
-    Env e;
-    e.tab = plant_tables_blob;
-    float obs[7], a[3];
-    env_reset(e, ar, env, obs);
-    const size_t traj = (size_t)actor * ar.n_envs + env;
-    while (!e.done) {
-        actor_forward_simple(w, ar.sh, bufA, bufB, tid, ROLLOUT_THREADS, obs, a);
-        env_step(e, ar, traj, a, obs);
-    }
-    ar.returns[traj] = e.ret;
-    ar.steps[traj] = e.k;
 }
 
 // ---- warp-autonomous actor + env ---------------------------------------------------------------------------
@@ -505,15 +531,14 @@ __device__ __forceinline__ void warp_layer(const float* __restrict__ Wt, const f
 
 __device__ __forceinline__ float group_sum(float v)
 {
-    v += __shfl_xor_sync(0xffffffffu, v, 1);
-    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, 1));
+    v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, 2));
     return v;
 }
 
 template <int H, int ACT>
 __device__ __noinline__ void actor_forward_warp(const float* __restrict__ w, int L, int lane, const float* obs, float* action)
 {
-    constexpr int actfn = ACT;
     constexpr int TM = H / 4, TM2 = H / 8;
     constexpr int S = 7, A = 3;
     const int og = lane & 3, gbase = lane & ~3;
@@ -547,10 +572,7 @@ __device__ __noinline__ void actor_forward_warp(const float* __restrict__ w, int
     for (int m2 = 0; m2 < TM2; ++m2) {
         const float2 b = *reinterpret_cast<const float2*>(b0 + og * TM + 2 * m2);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            in[m2][c].x = act_fn(actfn, acc[m2][c].x + b.x);
-            in[m2][c].y = act_fn(actfn, acc[m2][c].y + b.y);
-        }
+        for (int c = 0; c < 4; ++c) in[m2][c] = am_act2<ACT>(am_fma2(acc[m2][c], am_splat(1.0f), b));
     }
     // hidden layers: Linear -> LayerNorm (unbiased std, eps on std; mod_utils.py:47-50) -> activation
 #pragma unroll 1
@@ -566,34 +588,35 @@ __device__ __noinline__ void actor_forward_warp(const float* __restrict__ w, int
             const float2 b = *reinterpret_cast<const float2*>(bb + og * TM + 2 * m2);
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                acc[m2][c].x += b.x; s[c] += acc[m2][c].x;
-                acc[m2][c].y += b.y; s[c] += acc[m2][c].y;
+                acc[m2][c] = am_fma2(acc[m2][c], am_splat(1.0f), b);
+                s[c] = __fadd_rn(s[c], acc[m2][c].x);
+                s[c] = __fadd_rn(s[c], acc[m2][c].y);
             }
         }
         float mean[4], den[4];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) mean[c] = group_sum(s[c]) / (float)H;
+        for (int c = 0; c < 4; ++c) mean[c] = __fdiv_rn(group_sum(s[c]), (float)H);
         float q[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int m2 = 0; m2 < TM2; ++m2)
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                acc[m2][c].x -= mean[c]; q[c] = fmaf(acc[m2][c].x, acc[m2][c].x, q[c]);
-                acc[m2][c].y -= mean[c]; q[c] = fmaf(acc[m2][c].y, acc[m2][c].y, q[c]);
+                acc[m2][c] = am_fma2(acc[m2][c], am_splat(1.0f), am_splat(-mean[c]));
+                q[c] = __fmaf_rn(acc[m2][c].x, acc[m2][c].x, q[c]);
+                q[c] = __fmaf_rn(acc[m2][c].y, acc[m2][c].y, q[c]);
             }
-        // gamma * (x - mean) / (std + eps) + beta with one reciprocal per env instead of H/4 divisions per lane
-        // (<= 1 ulp from the reference's division, the same order as the summation-order differences of the GEMM)
+        // gamma * (x - mean) / (std + eps) + beta as fma(gamma * d, 1 / (std + eps), beta): one reciprocal per env instead
+        // of H/4 divisions per lane (<= 1 ulp from the reference's expression, the order of its summation-order freedom)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) den[c] = 1.0f / (sqrtf(group_sum(q[c]) / (float)(H - 1)) + 1e-6f);
+        for (int c = 0; c < 4; ++c)
+            den[c] = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(__fdiv_rn(group_sum(q[c]), (float)(H - 1))), 1e-6f));
 #pragma unroll
         for (int m2 = 0; m2 < TM2; ++m2) {
             const float2 g = *reinterpret_cast<const float2*>(gamma + og * TM + 2 * m2);
             const float2 be = *reinterpret_cast<const float2*>(beta + og * TM + 2 * m2);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                in[m2][c].x = act_fn(actfn, g.x * acc[m2][c].x * den[c] + be.x);
-                in[m2][c].y = act_fn(actfn, g.y * acc[m2][c].y * den[c] + be.y);
-            }
+            for (int c = 0; c < 4; ++c)
+                in[m2][c] = am_act2<ACT>(am_fma2(am_fma2(g, acc[m2][c], am_splat(-0.0f)), am_splat(den[c]), be));
         }
     }
     // output layer: partial dot products over this lane's neurons, reduced over the group; lane og keeps env 4g+og
@@ -604,87 +627,308 @@ __device__ __noinline__ void actor_forward_warp(const float* __restrict__ w, int
         for (int m2 = 0; m2 < TM2; ++m2) {
             const float2 wv = *reinterpret_cast<const float2*>(Wo + j * H + og * TM + 2 * m2);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) { p[c] = fmaf(wv.x, in[m2][c].x, p[c]); p[c] = fmaf(wv.y, in[m2][c].y, p[c]); }
+            for (int c = 0; c < 4; ++c) { p[c] = __fmaf_rn(wv.x, in[m2][c].x, p[c]); p[c] = __fmaf_rn(wv.y, in[m2][c].y, p[c]); }
         }
 #pragma unroll
         for (int c = 0; c < 4; ++c) p[c] = group_sum(p[c]);
         const float mine = og == 0 ? p[0] : (og == 1 ? p[1] : (og == 2 ? p[2] : p[3]));
-        action[j] = tanhf(mine + bo[j]);
+        action[j] = am_tanh1(__fadd_rn(mine, bo[j]));
     }
 }
 
+
+// ---- genome layout in shared memory -------------------------------------------------------------------------
+// parameters() order in HBM (row-major [out][in]) -> the kernel's layout (matrices transposed to [in][out]):
+//   Wt0[S][H] b0[H] | L x { Wt[H][H] b[H] gamma[H] beta[H] } | Wo[A][H] bo[A]
+__device__ __forceinline__ int genome_layout_index(int i, int S, int H, int L)
+{
+    int r = i;
+    if (r < S * H) { const int j = r / S, k = r % S; return k * H + j; }
+    r -= S * H;
+    if (r < H) return S * H + r;
+    r -= H;
+    const int per = H * H + 3 * H;
+    if (r < L * per) {
+        const int l = r / per, q = r % per;
+        const int base = S * H + H + l * per;
+        if (q < H * H) { const int j = q / H, k = q % H; return base + k * H + j; }
+        return base + q;
+    }
+    return i;      // Wo [A][H] then bo[A]: unchanged
+}
+
+// K0: all genomes of a launch into the shared-memory layout, rows padded to 16 bytes, so that the rollout kernel can
+// bring a genome into shared memory with ONE bulk TMA copy (cp.async.bulk) instead of a scattered staging loop.
+__global__ void genome_layout_kernel(const float* __restrict__ w, float* __restrict__ wt, int pop, int P, int P4, int S, int H, int L)
+{
+    const long long n = (long long)pop * P;
+    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < n; g += (long long)gridDim.x * blockDim.x) {
+        const int a = (int)(g / P), i = (int)(g % P);
+        wt[(size_t)a * P4 + genome_layout_index(i, S, H, L)] = w[g];
+    }
+}
+
+// ---- mbarrier / bulk-copy (TMA) primitives ----------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared bulk copy executed by the TMA unit; completion is signalled on the mbarrier as transferred bytes
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// ---- K1: persistent rollout ------------------------------------------------------------------------------------
+// grid = one CTA per SM (or fewer when there is less work); a CTA has `apc` genome slots of `wps` warps each.  A task is
+// (actor, chunk of wps*32 envs) x horizon steps.  Tasks are dealt to the slots as EQUAL SHARES OF STEPS: slot s owns
+// the range [s W/NS, (s+1) W/NS) of the linearised (task, step) space, W = n_tasks * horizon — i.e. possibly the tail of
+// one task, some whole tasks, and the head of another.  A slot flies the head segment FIRST and publishes the
+// trajectories' state in HBM (Handoff), then its whole tasks, and LAST the tail segment, whose first part the previous
+// slot published long before: no slot ever waits in practice, and all SMs finish together (512 actors x 128 envs on
+// 148 SMs x 2 slots = 1.73 tasks per slot: two full rounds without the split).  When there are fewer tasks than
+// slots every task is flown whole by one slot.  Warps never synchronise inside a segment; the slot's warps meet at a
+// named barrier only to swap the genome, which ONE elected thread brings in with a bulk TMA copy.
 // TABS: plant tables staged in shared memory (true) or read from global memory through L1 (false: h = 128, whose
 // 207 KB genome leaves no room for them).
-template <int H, int APC, bool TABS>
-__global__ void __launch_bounds__(ROLLOUT_THREADS * APC, 1)
-rollout_kernel_warp(RolloutArgs ar)
+template <int H, bool TABS>
+__global__ void __launch_bounds__(MAX_CTA_THREADS, 1)
+rollout_kernel_persist(RolloutArgs ar)
 {
-    constexpr int S = 7;
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ uint64_t gbar[4];                       // one mbarrier per genome slot
     real* tab_s = reinterpret_cast<real*>(smem_raw);
-    float* wbase = reinterpret_cast<float*>(tab_s + (TABS ? PT_TOTAL : 0));
+    constexpr int TABN = PT_TOTAL + SERL_PLANT_COUNT * PLANT_NPV;      // tables + per-variant parameter rows
+    constexpr int TABN2 = (TABN + 1) & ~1;
+    float* wbase = reinterpret_cast<float*>(tab_s + (TABS ? TABN2 : 0));
     const real* tab = TABS ? tab_s : plant_tables_blob;
+    const real* pv_base = TABS ? tab_s + PT_TOTAL : &plant_pv[0][0];
     const int L = ar.sh.num_layers;
-    const int P4 = (ar.P + 3) & ~3;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int al = warp >> 2;                               // actor slot of this warp inside the CTA
-    const int actor = blockIdx.y * APC + al;
-    const int env = blockIdx.x * ROLLOUT_THREADS + (warp & 3) * 32 + lane;
-    if (TABS)
-        for (int i = tid; i < PT_TOTAL; i += ROLLOUT_THREADS * APC) tab_s[i] = plant_tables_blob[i];
-    // stage the genomes: parameters() order in HBM (row-major [out][in]) -> transposed [in][out] in smem
-    for (int slot = 0; slot < APC; ++slot) {
-        const int ga = blockIdx.y * APC + slot;
-        if (ga >= ar.pop) break;
-        const float* gw = ar.weights + (size_t)ga * ar.P;
-        float* w = wbase + (size_t)slot * P4;
-        float* Wt0 = w; float* b0 = Wt0 + S * H; float* hid = b0 + H;
-        float* Wo = hid + (size_t)L * (H * H + 3 * H);
-        for (int i = tid; i < ar.P; i += ROLLOUT_THREADS * APC) {
-            const float v = gw[i];
-            int r = i;
-            if (r < S * H) { const int j = r / S, k = r % S; Wt0[k * H + j] = v; continue; }
-            r -= S * H;
-            if (r < H) { b0[r] = v; continue; }
-            r -= H;
-            const int per = H * H + 3 * H;
-            if (r < L * per) {
-                const int l = r / per, q = r % per;
-                float* base = hid + (size_t)l * per;
-                if (q < H * H) { const int j = q / H, k = q % H; base[k * H + j] = v; }
-                else base[q] = v;
-                continue;
-            }
-            r -= L * per;
-            Wo[r] = v;      // Wo [A][H] then bo[A], contiguous
-        }
+    const int wps = ar.wps;
+    const int slot_l = warp / wps, wslot = warp - slot_l * wps;
+    const long long slot = (long long)blockIdx.x * ar.apc + slot_l;
+    if (TABS) {
+        for (int i = tid; i < PT_TOTAL; i += blockDim.x) tab_s[i] = plant_tables_blob[i];
+        for (int i = tid; i < SERL_PLANT_COUNT * PLANT_NPV; i += blockDim.x) tab_s[PT_TOTAL + i] = (&plant_pv[0][0])[i];
+    }
+    if (tid == 0) {
+        for (int i = 0; i < ar.apc; ++i) mbar_init(&gbar[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (actor >= ar.pop) return;
-    const float* w = wbase + (size_t)al * P4;
-    Env e;
-    e.tab = tab;
-    float obs[7], a[3];
-    const bool valid = env < ar.n_envs && actor < ar.pop;
-    if (valid) env_reset(e, ar, env, obs);
-    else { e.done = true; e.k = 0; e.ret = 0.0;
-#pragma unroll
-        for (int i = 0; i < 7; ++i) obs[i] = 0.f; }
-    const size_t traj = valid ? (size_t)actor * ar.n_envs + env : 0;
+    float* w = wbase + (size_t)slot_l * ar.P4;
+    const int slot_threads = wps * 32;
     const int actfn = ar.sh.activation;
-    while (__any_sync(0xffffffffu, !e.done)) {
-        // one instantiation per activation: the choice is compiled into the 4 x h/4 activation calls of every layer
-        if (actfn == SERL_ACT_TANH) actor_forward_warp<H, SERL_ACT_TANH>(w, L, lane, obs, a);
-        else if (actfn == SERL_ACT_ELU) actor_forward_warp<H, SERL_ACT_ELU>(w, L, lane, obs, a);
-        else actor_forward_warp<H, SERL_ACT_LEAKY_RELU>(w, L, lane, obs, a);
-        if (!e.done) env_step(e, ar, traj, a, obs);
+    const int horizon = ar.horizon;
+    int cur_actor = -1;
+    uint32_t gphase = 0;
+
+    // this slot's share of the (task, step) space
+    const long long NT = ar.n_tasks, NS = ar.n_slots;
+    long long t_first, t_last;
+    int k0 = 0, k1 = 0;
+    if (NT <= NS) {
+        if (slot >= NT) return;
+        t_first = slot; t_last = slot + 1;
+    } else {
+        const long long W = NT * horizon;
+        const long long lo = slot * W / NS, hi = (slot + 1) * W / NS;
+        t_first = lo / horizon; t_last = hi / horizon;
+        k0 = (int)(lo - t_first * horizon); k1 = (int)(hi - t_last * horizon);
     }
-    if (valid) {
-        ar.returns[traj] = e.ret;
-        ar.steps[traj] = e.k;
+    // segments in the order: head of the last task (published) -> whole tasks -> tail of the first task (continued)
+    long long t_cur = t_first + (k0 > 0 ? 1 : 0);
+    int stage = 0;
+    for (;;) {
+        long long task;
+        int kb, ke;
+        bool from_h = false, to_h = false;
+        if (stage == 0) {
+            stage = 1;
+            if (k1 == 0) continue;
+            task = t_last; kb = 0; ke = k1; to_h = true;
+        } else if (stage == 1) {
+            if (t_cur >= t_last) { stage = 2; continue; }
+            task = t_cur++; kb = 0; ke = horizon;
+        } else if (stage == 2) {
+            stage = 3;
+            if (k0 == 0) continue;
+            task = t_first; kb = k0; ke = horizon; from_h = true;
+        } else break;
+        (void)kb;
+
+        const int actor = (int)(task / ar.n_chunks), chunk = (int)(task - (long long)actor * ar.n_chunks);
+        if (actor != cur_actor) {
+            // swap the genome of this slot: everyone has left the previous segment -> one thread launches the bulk copy
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + slot_l), "r"(slot_threads) : "memory");
+            if (wslot == 0 && lane == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads of w before the async write
+                const uint32_t bytes = (uint32_t)ar.P4 * 4u;
+                mbar_expect_tx(&gbar[slot_l], bytes);
+                tma_bulk_g2s(w, ar.wt + (size_t)actor * ar.P4, bytes, &gbar[slot_l]);
+            }
+            mbar_wait(&gbar[slot_l], gphase);
+            gphase ^= 1;
+            cur_actor = actor;
+        }
+        const int eslot = chunk * slot_threads + wslot * 32 + lane;
+        const bool valid = eslot < ar.n_envs;
+        const int env = valid ? (ar.env_order ? ar.env_order[eslot] : eslot) : 0;
+        Env e;
+        e.tab = tab;
+        float obs[7], a[3];
+        if (from_h) {      // the previous slot published this warp's trajectories when it STARTED; normally long done
+            if (lane == 0) {
+                const volatile int* f = ar.ho.flag + (slot - 1) * wps + wslot;
+                while (*f == 0) __nanosleep(200);
+            }
+            __syncwarp();
+            __threadfence();
+        }
+        if (valid) {
+            env_bind(e, ar, env, pv_base);
+            if (from_h) {
+                const long long hx = (slot - 1) * slot_threads + wslot * 32 + lane;
+#pragma unroll
+                for (int i = 0; i < NX; ++i) e.X[i] = __ldcg(ar.ho.X + (size_t)i * ar.ho.n + hx);
+                e.t = __ldcg(ar.ho.t + hx); e.ret = __ldcg(ar.ho.ret + hx);
+#pragma unroll
+                for (int i = 0; i < 7; ++i) obs[i] = __ldcg(ar.ho.obs + (size_t)i * ar.ho.n + hx);
+                const int kk = __ldcg(ar.ho.k + hx);
+                e.k = kk & 0x3fffffff; e.done = ((kk >> 30) & 1) != 0;
+            } else {
+                env_reset(e, ar, env, obs);
+            }
+        } else {
+            e.done = true; e.k = 0; e.ret = 0.0; e.t = 0.0; e.fault = 0; e.pv = pv_base; e.theta_trim = 0.0;
+            e.ref_lv = ar.ref_levels; e.ref_st = ar.ref_starts;
+#pragma unroll
+            for (int i = 0; i < NX; ++i) e.X[i] = 0.0;
+#pragma unroll
+            for (int i = 0; i < 7; ++i) obs[i] = 0.f;
+        }
+        const size_t traj = (size_t)actor * ar.n_envs + env;
+        const bool replay = valid && ar.replay != nullptr && env == ar.replay_env;
+        while (__any_sync(0xffffffffu, !e.done && e.k < ke)) {
+            // one instantiation per activation: the choice is compiled into the 4 x h/4 activation calls of every layer
+            if (actfn == SERL_ACT_TANH) actor_forward_warp<H, SERL_ACT_TANH>(w, L, lane, obs, a);
+            else if (actfn == SERL_ACT_ELU) actor_forward_warp<H, SERL_ACT_ELU>(w, L, lane, obs, a);
+            else actor_forward_warp<H, SERL_ACT_LEAKY_RELU>(w, L, lane, obs, a);
+            if (!e.done && e.k < ke) env_step(e, ar, traj, actor, replay, a, obs);
+        }
+        if (to_h) {
+            const long long hx = slot * slot_threads + wslot * 32 + lane;
+            if (valid) {
+#pragma unroll
+                for (int i = 0; i < NX; ++i) __stcg(ar.ho.X + (size_t)i * ar.ho.n + hx, e.X[i]);
+                __stcg(ar.ho.t + hx, e.t); __stcg(ar.ho.ret + hx, e.ret);
+#pragma unroll
+                for (int i = 0; i < 7; ++i) __stcg(ar.ho.obs + (size_t)i * ar.ho.n + hx, obs[i]);
+                __stcg(ar.ho.k + hx, e.k | ((e.done ? 1 : 0) << 30));
+            }
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) atomicExch(ar.ho.flag + slot * wps + wslot, 1);
+        } else if (valid) {
+            ar.returns[traj] = e.ret;
+            ar.steps[traj] = e.k;
+            if (ar.status && !isfinite(e.ret)) atomicOr(ar.status, SERL_STATUS_NONFINITE);
+        }
     }
 }
 
+// ---- cross-check kernel: every thread evaluates the whole MLP for its own env (any hidden size that fits) ------
+__global__ void __launch_bounds__(128)
+rollout_kernel_simple(RolloutArgs ar)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* w = reinterpret_cast<float*>(smem_raw);
+    const int P4 = (ar.P + 3) & ~3;
+    float* bufA = w + P4;
+    float* bufB = bufA + ar.sh.hidden * 128;
+    const int actor = blockIdx.y, tid = threadIdx.x;
+    const int eslot = blockIdx.x * 128 + tid;
+    const float* gw = ar.weights + (size_t)actor * ar.P;
+    for (int i = tid; i < ar.P; i += 128) w[i] = gw[i];
+    __syncthreads();
+    if (eslot >= ar.n_envs) return;
+    const int env = ar.env_order ? ar.env_order[eslot] : eslot;
+    Env e;
+    e.tab = plant_tables_blob;
+    float obs[7], a[3];
+    env_bind(e, ar, env, &plant_pv[0][0]);
+    env_reset(e, ar, env, obs);
+    const size_t traj = (size_t)actor * ar.n_envs + env;
+    const bool replay = ar.replay != nullptr && env == ar.replay_env;
+    while (!e.done) {
+        actor_forward_simple(w, ar.sh, bufA, bufB, tid, 128, obs, a);
+        env_step(e, ar, traj, actor, replay, a, obs);
+    }
+    ar.returns[traj] = e.ret;
+    ar.steps[traj] = e.k;
+    if (ar.status && !isfinite(e.ret)) atomicOr(ar.status, SERL_STATUS_NONFINITE);
+}
+
+// ---- Actor.forward for a batch of observations (same device functions as the rollout) --------------------------
+template <int H>
+__global__ void __launch_bounds__(128)
+actor_forward_kernel(const float* __restrict__ genome, int P, serl_actor_shape sh, const float* __restrict__ obs_in, int n,
+                     float* __restrict__ act_out)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* w = reinterpret_cast<float*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int i = tid; i < P; i += 128) w[genome_layout_index(i, sh.state_dim, H, sh.num_layers)] = genome[i];
+    __syncthreads();
+    const int base = (blockIdx.x * 128 + (tid & ~31));
+    if (base >= n) return;
+    const int i = base + lane;
+    float obs[7], a[3];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) obs[k] = i < n ? obs_in[(size_t)i * 7 + k] : 0.f;
+    if (sh.activation == SERL_ACT_TANH) actor_forward_warp<H, SERL_ACT_TANH>(w, sh.num_layers, lane, obs, a);
+    else if (sh.activation == SERL_ACT_ELU) actor_forward_warp<H, SERL_ACT_ELU>(w, sh.num_layers, lane, obs, a);
+    else actor_forward_warp<H, SERL_ACT_LEAKY_RELU>(w, sh.num_layers, lane, obs, a);
+    if (i < n) { act_out[(size_t)i * 3] = a[0]; act_out[(size_t)i * 3 + 1] = a[1]; act_out[(size_t)i * 3 + 2] = a[2]; }
+}
+
+__global__ void __launch_bounds__(128)
+actor_forward_kernel_simple(const float* __restrict__ genome, int P, serl_actor_shape sh, const float* __restrict__ obs_in, int n,
+                            float* __restrict__ act_out)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* w = reinterpret_cast<float*>(smem_raw);
+    float* bufA = w + ((P + 3) & ~3);
+    float* bufB = bufA + sh.hidden * 128;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < P; i += 128) w[i] = genome[i];
+    __syncthreads();
+    const int i = blockIdx.x * 128 + tid;
+    if (i >= n) return;
+    float obs[7], a[3];
+    for (int k = 0; k < 7; ++k) obs[k] = obs_in[(size_t)i * 7 + k];
+    actor_forward_simple(w, sh, bufA, bufB, tid, 128, obs, a);
+    act_out[(size_t)i * 3] = a[0]; act_out[(size_t)i * 3 + 1] = a[1]; act_out[(size_t)i * 3 + 2] = a[2];
+}
 // fitness[a] = mean over envs of returns[a, :]  (base/core/agent.py:245, np.mean over the evaluation axis)
 __global__ void fitness_mean_kernel(const double* __restrict__ returns, int pop, int n_envs, double* __restrict__ fitness)
 {
@@ -704,7 +948,7 @@ __global__ void plant_step_kernel(double* __restrict__ X, const double* __restri
 #pragma unroll
     for (int k = 0; k < NX; ++k) x[k] = X[(size_t)i * NX + k];
     u[0] = cmd[3 * i]; u[1] = cmd[3 * i + 1]; u[2] = cmd[3 * i + 2];
-    plant_step(variant[i] & 0xff, x, u, plant_tables_blob);
+    plant_step(plant_pv[variant[i] & 0xff], x, u, plant_tables_blob);
 #pragma unroll
     for (int k = 0; k < NX; ++k) X[(size_t)i * NX + k] = x[k];
 }
@@ -828,32 +1072,193 @@ extern "C" int64_t serl_actor_num_params(const serl_actor_shape* s)
 }
 
 static int g_force_simple = -1;
-
-template <int H, int APC, bool TABS>
-static cudaError_t launch_warp(const RolloutArgs& ar, cudaStream_t s)
+static int env_int(const char* name)
 {
-    const int P4 = (ar.P + 3) & ~3;
-    const size_t smem = (TABS ? (size_t)PT_TOTAL * sizeof(real) : 0) + (size_t)APC * P4 * 4;
-    cudaError_t e = cudaFuncSetAttribute(rollout_kernel_warp<H, APC, TABS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const char* v = getenv(name);
+    return v ? atoi(v) : 0;
+}
+
+static int device_sms()
+{
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
+    }
+    return num_sms;
+}
+
+// CTA shape of the persistent kernel: `apc` genome slots x `wps` warps.  A slot's warps fly wps*32 envs of one actor;
+// the estimate below is (rounds of work per slot) x (time of one step with apc*wps resident warps per SM), the latter a
+// linear fit of measurements at 4 and 8 warps (profiles/): a lone warp steps 1.4x faster than one of eight.
+static void choose_shape(int pop, int n_envs, int apc_max, int sms, int* apc_out, int* wps_out)
+{
+    double best = 1e300;
+    *apc_out = 1; *wps_out = 1;
+    const int max_wps = (n_envs + 31) / 32;
+    for (int wps = 4; wps >= 1; wps >>= 1) {
+        if (wps > max_wps && wps > 1) continue;
+        const long long chunks = (n_envs + wps * 32 - 1) / (wps * 32);
+        const long long nt = (long long)pop * chunks;
+        for (int apc = apc_max; apc >= 1; --apc) {
+            if (apc * wps * 32 > MAX_CTA_THREADS) continue;
+            const long long grid = nt / apc < sms ? (nt + apc - 1) / apc : sms;
+            const long long ns = grid * apc;
+            const double rounds = nt <= ns ? 1.0 : (double)nt / (double)ns;
+            const double lanes = (double)chunks * wps * 32 / n_envs;        // idle-lane overhead of a ragged last chunk
+            const double est = rounds * (13.2 + 0.825 * apc * wps) * (lanes > 1.0 ? 1.0 + 0.2 * (lanes - 1.0) : 1.0);
+            if (est < best - 1e-9) { best = est; *apc_out = apc; *wps_out = wps; }
+        }
+    }
+}
+
+template <int H, bool TABS>
+static cudaError_t launch_persist(RolloutArgs& ar, int apc_max, cudaStream_t s, void** scratch)
+{
+    constexpr int TABN2 = (PT_TOTAL + SERL_PLANT_COUNT * PLANT_NPV + 1) & ~1;
+    const int sms = device_sms();
+    int apc, wps;
+    choose_shape(ar.pop, ar.n_envs, apc_max, sms, &apc, &wps);
+    static int f_apc = -1, f_wps = -1;       // experiment knobs
+    if (f_apc < 0) { f_apc = env_int("SERL_ROLLOUT_APC"); f_wps = env_int("SERL_ROLLOUT_WPS"); }
+    if (f_apc > 0 && f_apc <= apc_max) apc = f_apc;
+    if (f_wps == 1 || f_wps == 2 || f_wps == 4) wps = f_wps;
+    while (apc * wps * 32 > MAX_CTA_THREADS) --apc;
+    ar.apc = apc; ar.wps = wps;
+    ar.n_chunks = (ar.n_envs + wps * 32 - 1) / (wps * 32);
+    ar.n_tasks = (long long)ar.pop * ar.n_chunks;
+    const long long grid = ar.n_tasks / apc < sms ? (ar.n_tasks + apc - 1) / apc : sms;
+    ar.n_slots = grid * apc;
+    // scratch: genomes in the shared-memory layout + hand-over records of the time-split schedule (stream-ordered)
+    const size_t wt_bytes = (size_t)ar.pop * ar.P4 * 4;
+    const long long hn = ar.n_tasks > ar.n_slots ? ar.n_slots * wps * 32 : 0;
+    const size_t ho_bytes = (size_t)hn * (NX * 8 + 8 + 8 + 7 * 4 + 4) + (size_t)(hn / 32) * 4;
+    cudaError_t e = cudaMallocAsync(scratch, wt_bytes + ho_bytes + 256, s);
     if (e != cudaSuccess) return e;
-    dim3 grid((ar.n_envs + ROLLOUT_THREADS - 1) / ROLLOUT_THREADS, (ar.pop + APC - 1) / APC);
-    rollout_kernel_warp<H, APC, TABS><<<grid, ROLLOUT_THREADS * APC, smem, s>>>(ar);
+    unsigned char* base = (unsigned char*)*scratch;
+    float* wt = (float*)base;
+    ar.wt = wt;
+    ar.ho.n = hn;
+    if (hn) {
+        unsigned char* p = base + ((wt_bytes + 255) & ~(size_t)255);
+        ar.ho.X = (double*)p; p += (size_t)hn * NX * 8;
+        ar.ho.t = (double*)p; p += (size_t)hn * 8;
+        ar.ho.ret = (double*)p; p += (size_t)hn * 8;
+        ar.ho.obs = (float*)p; p += (size_t)hn * 7 * 4;
+        ar.ho.k = (int*)p; p += (size_t)hn * 4;
+        ar.ho.flag = (int*)p;
+        e = cudaMemsetAsync(ar.ho.flag, 0, (size_t)(hn / 32) * 4, s);
+        if (e != cudaSuccess) return e;
+    }
+    const long long n = (long long)ar.pop * ar.P;
+    const int lay_grid = (int)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096);
+    genome_layout_kernel<<<lay_grid, 256, 0, s>>>(ar.weights, wt, ar.pop, ar.P, ar.P4, ar.sh.state_dim, H, ar.sh.num_layers);
+    serl_count_launch();
+    const size_t smem = (TABS ? (size_t)TABN2 * sizeof(real) : 0) + (size_t)apc * ar.P4 * 4;
+    e = cudaFuncSetAttribute(rollout_kernel_persist<H, TABS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    rollout_kernel_persist<H, TABS><<<(unsigned)grid, apc * wps * 32, smem, s>>>(ar);
+    serl_count_launch();
     return cudaGetLastError();
 }
 
-static int rollout_impl(const float* d_weights, int32_t pop, const serl_actor_shape* shape,
-                        const double* d_ref_levels, const double* d_ref_starts, const int32_t* d_env_mode,
-                        int32_t n_envs, int32_t horizon, const float* d_action_noise,
-                        double* d_returns, int32_t* d_steps, double* d_fitness, double* d_trace, float* d_actions,
-                        double t_max, double smooth_w, void* stream);
+static int rollout_impl(const serl_rollout_desc& d, void* stream)
+{
+    const serl_actor_shape* shape = &d.shape;
+    if (!d.d_weights || !d.d_ref_levels || !d.d_ref_starts || !d.d_env_mode || !d.d_returns || !d.d_steps)
+        return serl_fail(SERL_ERR_ARG, "serl_rollout: null pointer argument");
+    if (d.pop <= 0 || d.n_envs <= 0 || d.horizon <= 0) return serl_fail(SERL_ERR_ARG, "serl_rollout: pop, n_envs, horizon must be > 0");
+    if (d.pop > 65535) return serl_fail(SERL_ERR_ARG, "serl_rollout: pop must be <= 65535 per call");
+    if (shape->state_dim != 7 || shape->action_dim != 3)
+        return serl_fail(SERL_ERR_ARG, "serl_rollout: PH-LAB attitude task needs state_dim=7, action_dim=3");
+    if (shape->hidden < 2 || shape->hidden > 256 || shape->num_layers < 0 || shape->activation < 0 || shape->activation > 2)
+        return serl_fail(SERL_ERR_ARG, "serl_rollout: unsupported actor shape");
+    if (d.d_replay && (d.replay_env < 0 || d.replay_env >= d.n_envs)) return serl_fail(SERL_ERR_ARG, "serl_rollout: replay_env out of range");
+    if (d.horizon >= (1 << 30)) return serl_fail(SERL_ERR_ARG, "serl_rollout: horizon too long");
+    if (g_force_simple < 0) {
+        const char* v = getenv("SERL_ROLLOUT_IMPL");
+        g_force_simple = (v && strcmp(v, "simple") == 0) ? 1 : 0;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    RolloutArgs ar;
+    memset(&ar, 0, sizeof(ar));
+    ar.weights = d.d_weights; ar.P = (int)serl_actor_num_params(shape); ar.sh = *shape;
+    ar.ref_levels = d.d_ref_levels; ar.ref_starts = d.d_ref_starts; ar.env_mode = d.d_env_mode; ar.n_envs = d.n_envs; ar.horizon = d.horizon;
+    ar.action_noise = d.d_action_noise; ar.returns = d.d_returns; ar.steps = d.d_steps; ar.trace = d.d_trace; ar.actions = d.d_actions;
+    ar.pop = d.pop;
+    ar.t_max = d.t_max > 0.0 ? d.t_max : 20.0;
+    ar.smooth_w = d.t_max > 0.0 ? d.smooth_width : 3.0;
+    ar.env_order = d.d_env_order; ar.replay = d.d_replay; ar.replay_env = d.replay_env; ar.status = d.d_status;
+    ar.P4 = (ar.P + 3) & ~3;
+    const int H = shape->hidden;
+    cudaError_t e;
+    const size_t tab_bytes = (size_t)((PT_TOTAL + SERL_PLANT_COUNT * PLANT_NPV + 1) & ~1) * sizeof(real);
+    const bool warp_ok = !g_force_simple && (H == 32 || H == 64 || H == 72 || H == 96 || H == 128) && (size_t)ar.P4 * 4 <= 227 * 1024;
+    if (warp_ok) {
+        // as many genome slots per CTA as shared memory holds next to the plant tables (h <= 72: two; h = 96: one);
+        // h = 128 (207 KB genome) reads the tables through L1 instead
+        const size_t budget = 227 * 1024 - 64;
+        const bool tabs = tab_bytes + (size_t)ar.P4 * 4 <= budget;
+        int apc_max = (int)(((tabs ? budget - tab_bytes : budget)) / ((size_t)ar.P4 * 4));
+        if (apc_max > 4) apc_max = 4;
+        if (apc_max > 2 && H > 32) apc_max = 2;
+        void* scratch = nullptr;
+        if (H == 32) e = launch_persist<32, true>(ar, apc_max, s, &scratch);
+        else if (H == 64) e = launch_persist<64, true>(ar, apc_max, s, &scratch);
+        else if (H == 72) e = launch_persist<72, true>(ar, apc_max, s, &scratch);
+        else if (H == 96) e = launch_persist<96, true>(ar, apc_max, s, &scratch);
+        else e = tabs ? launch_persist<128, true>(ar, apc_max, s, &scratch) : launch_persist<128, false>(ar, apc_max, s, &scratch);
+        if (scratch) cudaFreeAsync(scratch, s);
+    } else {
+        const size_t smem = (size_t)ar.P4 * 4 + 2ull * H * 128 * 4;
+        if (smem > 227 * 1024) return serl_fail(SERL_ERR_UNSUPPORTED, "serl_rollout: genome + activations exceed 227 KB of shared memory");
+        e = cudaFuncSetAttribute(rollout_kernel_simple, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return serl_fail_cuda(e, "cudaFuncSetAttribute(rollout)");
+        dim3 grid((d.n_envs + 127) / 128, d.pop);
+        rollout_kernel_simple<<<grid, 128, smem, s>>>(ar);
+        serl_count_launch();
+        e = cudaGetLastError();
+    }
+    if (e != cudaSuccess) return serl_fail_cuda(e, "rollout_kernel launch");
+    if (d.d_fitness) {
+        fitness_mean_kernel<<<(d.pop + 127) / 128, 128, 0, s>>>(d.d_returns, d.pop, d.n_envs, d.d_fitness);
+        serl_count_launch();
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return serl_fail_cuda(e, "fitness_mean_kernel launch");
+    }
+    return SERL_OK;
+}
+
+extern "C" int serl_rollout_run(const serl_rollout_desc* desc, void* stream)
+{
+    if (!desc) return serl_fail(SERL_ERR_ARG, "serl_rollout_run: null descriptor");
+    if (desc->t_max > 0.0 && !(desc->smooth_width > 0.0)) return serl_fail(SERL_ERR_ARG, "serl_rollout_run: smooth_width must be > 0");
+    return rollout_impl(*desc, stream);
+}
+
+static serl_rollout_desc make_desc(const float* d_weights, int32_t pop, const serl_actor_shape* shape,
+                                   const double* d_ref_levels, const double* d_ref_starts, const int32_t* d_env_mode,
+                                   int32_t n_envs, int32_t horizon, const float* d_action_noise,
+                                   double* d_returns, int32_t* d_steps, double* d_fitness, double* d_trace, float* d_actions)
+{
+    serl_rollout_desc d;
+    memset(&d, 0, sizeof(d));
+    d.d_weights = d_weights; d.pop = pop; if (shape) d.shape = *shape;
+    d.d_ref_levels = d_ref_levels; d.d_ref_starts = d_ref_starts; d.d_env_mode = d_env_mode; d.n_envs = n_envs; d.horizon = horizon;
+    d.d_action_noise = d_action_noise; d.d_returns = d_returns; d.d_steps = d_steps; d.d_fitness = d_fitness; d.d_trace = d_trace;
+    d.d_actions = d_actions;
+    return d;
+}
 
 extern "C" int serl_rollout(const float* d_weights, int32_t pop, const serl_actor_shape* shape,
                             const double* d_ref_levels, const double* d_ref_starts, const int32_t* d_env_mode,
                             int32_t n_envs, int32_t horizon, const float* d_action_noise,
                             double* d_returns, int32_t* d_steps, double* d_fitness, double* d_trace, float* d_actions, void* stream)
 {
-    return rollout_impl(d_weights, pop, shape, d_ref_levels, d_ref_starts, d_env_mode, n_envs, horizon, d_action_noise,
-                        d_returns, d_steps, d_fitness, d_trace, d_actions, 20.0, 3.0, stream);
+    if (!shape) return serl_fail(SERL_ERR_ARG, "serl_rollout: null pointer argument");
+    return rollout_impl(make_desc(d_weights, pop, shape, d_ref_levels, d_ref_starts, d_env_mode, n_envs, horizon, d_action_noise,
+                                  d_returns, d_steps, d_fitness, d_trace, d_actions), stream);
 }
 
 extern "C" int serl_rollout_eval(const float* d_weights, int32_t pop, const serl_actor_shape* shape,
@@ -862,80 +1267,44 @@ extern "C" int serl_rollout_eval(const float* d_weights, int32_t pop, const serl
                                  double* d_returns, int32_t* d_steps, double* d_fitness, double* d_trace, float* d_actions,
                                  double t_max, double smooth_width, void* stream)
 {
+    if (!shape) return serl_fail(SERL_ERR_ARG, "serl_rollout_eval: null pointer argument");
     if (!(t_max > 0.0) || !(smooth_width > 0.0)) return serl_fail(SERL_ERR_ARG, "serl_rollout_eval: t_max and smooth_width must be > 0");
-    return rollout_impl(d_weights, pop, shape, d_ref_levels, d_ref_starts, d_env_mode, n_envs, horizon, d_action_noise,
-                        d_returns, d_steps, d_fitness, d_trace, d_actions, t_max, smooth_width, stream);
+    serl_rollout_desc d = make_desc(d_weights, pop, shape, d_ref_levels, d_ref_starts, d_env_mode, n_envs, horizon, d_action_noise,
+                                    d_returns, d_steps, d_fitness, d_trace, d_actions);
+    d.t_max = t_max; d.smooth_width = smooth_width;
+    return rollout_impl(d, stream);
 }
 
-static int rollout_impl(const float* d_weights, int32_t pop, const serl_actor_shape* shape,
-                        const double* d_ref_levels, const double* d_ref_starts, const int32_t* d_env_mode,
-                        int32_t n_envs, int32_t horizon, const float* d_action_noise,
-                        double* d_returns, int32_t* d_steps, double* d_fitness, double* d_trace, float* d_actions,
-                        double t_max, double smooth_w, void* stream)
+extern "C" int serl_actor_forward(const float* d_genome, const serl_actor_shape* shape, const float* d_obs, int32_t n,
+                                  float* d_actions, void* stream)
 {
-    if (!d_weights || !shape || !d_ref_levels || !d_ref_starts || !d_env_mode || !d_returns || !d_steps)
-        return serl_fail(SERL_ERR_ARG, "serl_rollout: null pointer argument");
-    if (pop <= 0 || n_envs <= 0 || horizon <= 0) return serl_fail(SERL_ERR_ARG, "serl_rollout: pop, n_envs, horizon must be > 0");
-    if (pop > 65535) return serl_fail(SERL_ERR_ARG, "serl_rollout: pop must be <= 65535 per call");
-    if (shape->state_dim != 7 || shape->action_dim != 3)
-        return serl_fail(SERL_ERR_ARG, "serl_rollout: PH-LAB attitude task needs state_dim=7, action_dim=3");
-    if (shape->hidden < 2 || shape->hidden > 256 || shape->num_layers < 0 || shape->activation < 0 || shape->activation > 2)
-        return serl_fail(SERL_ERR_ARG, "serl_rollout: unsupported actor shape");
+    if (!d_genome || !shape || !d_obs || !d_actions || n <= 0) return serl_fail(SERL_ERR_ARG, "serl_actor_forward: bad argument");
+    if (shape->state_dim != 7 || shape->action_dim != 3 || shape->hidden < 2 || shape->hidden > 256 || shape->num_layers < 0 ||
+        shape->activation < 0 || shape->activation > 2)
+        return serl_fail(SERL_ERR_ARG, "serl_actor_forward: unsupported actor shape");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int P = (int)serl_actor_num_params(shape), H = shape->hidden;
+    const int grid = (n + 127) / 128;
+    cudaError_t e = cudaSuccess;
+    const size_t smem = (size_t)((P + 3) & ~3) * 4;
+#define AF_LAUNCH(HH) do { e = cudaFuncSetAttribute(actor_forward_kernel<HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e == cudaSuccess) { actor_forward_kernel<HH><<<grid, 128, smem, s>>>(d_genome, P, *shape, d_obs, n, d_actions); e = cudaGetLastError(); } } while (0)
     if (g_force_simple < 0) {
         const char* v = getenv("SERL_ROLLOUT_IMPL");
         g_force_simple = (v && strcmp(v, "simple") == 0) ? 1 : 0;
     }
-    cudaStream_t s = (cudaStream_t)stream;
-    RolloutArgs ar;
-    ar.weights = d_weights; ar.P = (int)serl_actor_num_params(shape); ar.sh = *shape;
-    ar.ref_levels = d_ref_levels; ar.ref_starts = d_ref_starts; ar.env_mode = d_env_mode; ar.n_envs = n_envs; ar.horizon = horizon;
-    ar.action_noise = d_action_noise; ar.returns = d_returns; ar.steps = d_steps; ar.trace = d_trace; ar.actions = d_actions; ar.pop = pop; ar.t_max = t_max; ar.smooth_w = smooth_w;
-    const int P4 = (ar.P + 3) & ~3;
-    const int H = shape->hidden;
-    dim3 grid((n_envs + ROLLOUT_THREADS - 1) / ROLLOUT_THREADS, pop);
-    cudaError_t e;
-    const bool warp_ok = !g_force_simple && (H == 32 || H == 64 || H == 72 || H == 96 || H == 128) && (size_t)P4 * 4 <= 227 * 1024;
-    if (warp_ok) {
-        // two actors per CTA (8 autonomous warps) when two genomes + the plant tables fit in shared memory; one actor
-        // with the tables in shared memory when that fits; else (h = 128) one actor and the tables through L1
-        // ... and when that still leaves at least one CTA per SM: a small population spreads over more SMs with one
-        // actor per CTA (4 warps each) instead of filling half as many SMs with 8 warps
-        static int num_sms = 0;
-        if (num_sms == 0) {
-            int dev = 0;
-            cudaGetDevice(&dev);
-            if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
-        }
-        const long ctas2 = (long)((pop + 1) / 2) * ((n_envs + ROLLOUT_THREADS - 1) / ROLLOUT_THREADS);
-        const bool two = (size_t)PT_TOTAL * sizeof(real) + 2ull * P4 * 4 <= 227 * 1024 && pop > 1 && ctas2 >= num_sms;
-        const bool tabs = (size_t)PT_TOTAL * sizeof(real) + (size_t)P4 * 4 <= 227 * 1024;
-        static int apc_exp = -1;          // experiment knob (SERL_ROLLOUT_APC=3|4, h = 32 only): more resident warps per SM
-        if (apc_exp < 0) { const char* v = getenv("SERL_ROLLOUT_APC"); apc_exp = v ? atoi(v) : 0; }
-        if (H == 32 && apc_exp == 3 && pop > 2) e = launch_warp<32, 3, true>(ar, s);
-        else if (H == 32 && apc_exp == 4 && pop > 3) e = launch_warp<32, 4, true>(ar, s);
-        else if (H == 32) e = two ? launch_warp<32, 2, true>(ar, s) : launch_warp<32, 1, true>(ar, s);
-        else if (H == 64) e = two ? launch_warp<64, 2, true>(ar, s) : launch_warp<64, 1, true>(ar, s);
-#ifdef PLANT_F32
-        else if (H == 72 && apc_exp == 3 && pop > 2) e = launch_warp<72, 3, true>(ar, s);   // float tables: three genomes fit
-#endif
-        else if (H == 72) e = two ? launch_warp<72, 2, true>(ar, s) : launch_warp<72, 1, true>(ar, s);
-        else if (H == 96) e = launch_warp<96, 1, true>(ar, s);
-        else e = tabs ? launch_warp<128, 1, true>(ar, s) : launch_warp<128, 1, false>(ar, s);
-    } else {
-        const size_t smem = (size_t)P4 * 4 + 2ull * H * ROLLOUT_THREADS * 4;
-        if (smem > 227 * 1024) return serl_fail(SERL_ERR_UNSUPPORTED, "serl_rollout: genome + activations exceed 227 KB of shared memory");
-        e = cudaFuncSetAttribute(rollout_kernel_simple, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return serl_fail_cuda(e, "cudaFuncSetAttribute(rollout)");
-        rollout_kernel_simple<<<grid, ROLLOUT_THREADS, smem, s>>>(ar);
-        e = cudaGetLastError();
+    if (!g_force_simple && H == 32) AF_LAUNCH(32);
+    else if (!g_force_simple && H == 64) AF_LAUNCH(64);
+    else if (!g_force_simple && H == 72) AF_LAUNCH(72);
+    else if (!g_force_simple && H == 96) AF_LAUNCH(96);
+    else if (!g_force_simple && H == 128) AF_LAUNCH(128);
+    else {
+        const size_t sm2 = smem + 2ull * H * 128 * 4;
+        if (sm2 > 227 * 1024) return serl_fail(SERL_ERR_UNSUPPORTED, "serl_actor_forward: genome + activations exceed shared memory");
+        e = cudaFuncSetAttribute(actor_forward_kernel_simple, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
+        if (e == cudaSuccess) { actor_forward_kernel_simple<<<grid, 128, sm2, s>>>(d_genome, P, *shape, d_obs, n, d_actions); e = cudaGetLastError(); }
     }
+#undef AF_LAUNCH
     serl_count_launch();
-    if (e != cudaSuccess) return serl_fail_cuda(e, "rollout_kernel launch");
-    if (d_fitness) {
-        fitness_mean_kernel<<<(pop + 127) / 128, 128, 0, s>>>(d_returns, pop, n_envs, d_fitness);
-        serl_count_launch();
-        e = cudaGetLastError();
-        if (e != cudaSuccess) return serl_fail_cuda(e, "fitness_mean_kernel launch");
-    }
-    return SERL_OK;
+    return e == cudaSuccess ? SERL_OK : serl_fail_cuda(e, "actor_forward_kernel");
 }

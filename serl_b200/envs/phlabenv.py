@@ -25,11 +25,11 @@ class Box:
 
 
 class _RefSignal:
-    def __init__(self, levels, starts, offset, smooth_w=refsig.SMOOTH_W):
-        self.levels, self.starts, self.offset, self.smooth_w = levels, starts, offset, smooth_w
+    def __init__(self, levels, starts, offset, smooth_w=refsig.SMOOTH_W, t_end=None):
+        self.levels, self.starts, self.offset, self.smooth_w, self.t_end = levels, starts, offset, smooth_w, t_end
 
     def __call__(self, t):
-        return refsig.ref_value_deg(self.levels, self.starts, t, self.offset, self.smooth_w)
+        return refsig.ref_value_deg(self.levels, self.starts, t, self.offset, self.smooth_w, self.t_end)
 
 
 class CitationEnv:
@@ -133,7 +133,7 @@ class CitationEnv:
         self.levels, self.starts = self.draw_reference()
         self.theta_trim = np.rad2deg(self.x[7])
         sw = refsig.widths(self.t_max)[1]
-        self.ref = [_RefSignal(self.levels[0], self.starts[0], self.theta_trim, sw),
+        self.ref = [_RefSignal(self.levels[0], self.starts[0], self.theta_trim, sw, self.t_max),
                     _RefSignal(self.levels[1], self.starts[1], 0.0, sw), lambda t: 0.0]
 
     # ---- native plant on the device ----

@@ -41,8 +41,13 @@ def make_ref_params(n_envs, seed_base=7_000_000, t_max=20):
     return levels, starts
 
 
-def ref_value_deg(levels, starts, t, offset=0.0, smooth_w=SMOOTH_W):
-    """value [deg] of one channel at time t. levels/starts: [N_BLOCKS]."""
+def ref_value_deg(levels, starts, t, offset=0.0, smooth_w=SMOOTH_W, t_end=None):
+    """value [deg] of one channel at time t. levels/starts: [N_BLOCKS].  `offset` is the reference's
+    `+ signals.Const(0., t_max, theta_trim)` (envs/phlabenv.py:344): a constant that exists on [0, t_max] only — the last
+    row of every logged episode (t = 20.01 s) shows the step sequence without it, and so does the final step of an
+    episode, whose accumulated time is 20.000000000000327 s."""
+    if t_end is not None and t > t_end:
+        offset = 0.0
     k = 0
     for j in range(1, N_BLOCKS):
         if t >= starts[j]:

@@ -38,7 +38,7 @@ def _ptr(t):
 
 
 class RolloutResult:
-    __slots__ = ('returns', 'steps', 'fitness', 'trace', 'actions', 'smoothness')
+    __slots__ = ('returns', 'steps', 'fitness', 'trace', 'actions', 'smoothness', 'replay', 'status')
 
     # views into the trace record (include/serl_b200.h: SERL_TRACE_COLS)
     trace_x = property(lambda s: s.trace[..., 0:12])
@@ -47,13 +47,27 @@ class RolloutResult:
     trace_a = property(lambda s: s.trace[..., 16:19])
     trace_err = property(lambda s: s.trace[..., 19:22])
 
+    def check(self):
+        """raise if the kernel flagged a non-finite trajectory (synchronises the device)."""
+        if self.status is not None and int(self.status.item()) & _native.STATUS_NONFINITE:
+            raise _native.NativeError('serl_rollout: a trajectory produced a non-finite state / return (status flag)')
+
 
 TRACE_COLS = 22
+REPLAY_COLS = _native.REPLAY_COLS
+
+
+def variant_sorted_order(env_mode):
+    """permutation that groups envs by mode (plant variant, fault shim): the 32 lanes of a warp then share the shim's
+    branch and the variant's parameter row.  Results are still written at each env's own index."""
+    return torch.argsort(env_mode, stable=True).to(torch.int32)
 
 
 def population_rollout(weights, shape, ref_levels, ref_starts, env_mode, horizon=HORIZON, trace=False, out=None, action_noise=None,
-                       actions=False, t_max=None, smooth_width=None):
-    """weights [pop,P] fp32 cuda; ref_levels/ref_starts [n_envs,2,6] f64 cuda; env_mode [n_envs] int32 cuda."""
+                       actions=False, t_max=None, smooth_width=None, env_order=None, replay_env=None, status=True):
+    """weights [pop,P] fp32 cuda; ref_levels/ref_starts [n_envs,2,6] f64 cuda; env_mode [n_envs] int32 cuda.
+    env_order: optional int32 [n_envs] permutation (see variant_sorted_order); replay_env: record the transitions of that env
+    of every actor into result.replay [pop, horizon, REPLAY_COLS]; status: carry the device status word (result.check())."""
     if not weights.is_cuda:
         raise _native.NativeError('population_rollout needs CUDA tensors (no CPU fallback)')
     L = _native.lib()
@@ -66,6 +80,8 @@ def population_rollout(weights, shape, ref_levels, ref_starts, env_mode, horizon
     assert env_mode.dtype == torch.int32
     if action_noise is not None:
         assert action_noise.shape == (pop, n_envs, horizon, 3) and action_noise.dtype == torch.float32 and action_noise.is_contiguous()
+    if env_order is not None:
+        assert env_order.shape == (n_envs,) and env_order.dtype == torch.int32 and env_order.is_cuda
     dev = weights.device
     r = out if out is not None else RolloutResult()
     if out is None:
@@ -73,19 +89,43 @@ def population_rollout(weights, shape, ref_levels, ref_starts, env_mode, horizon
         r.steps = torch.empty((pop, n_envs), dtype=torch.int32, device=dev)
         r.fitness = torch.empty((pop,), dtype=torch.float64, device=dev)
         r.trace = None
+        r.smoothness = None
         r.actions = torch.empty((pop, n_envs, horizon, 3), dtype=torch.float32, device=dev) if actions else None
+        r.replay = torch.empty((pop, horizon, REPLAY_COLS), dtype=torch.float32, device=dev) if replay_env is not None else None
+        r.status = torch.zeros((1,), dtype=torch.int32, device=dev) if status else None
         if trace:
             r.trace = torch.full((pop, n_envs, horizon, TRACE_COLS), float('nan'), dtype=torch.float64, device=dev)
+    elif r.status is not None:
+        r.status.zero_()
     stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-    args = (_ptr(weights), pop, ctypes.byref(shape), _ptr(ref_levels), _ptr(ref_starts), _ptr(env_mode),
-            n_envs, horizon, _ptr(action_noise), _ptr(r.returns), _ptr(r.steps), _ptr(r.fitness),
-            _ptr(r.trace), _ptr(getattr(r, 'actions', None)))
-    if t_max is None:
-        rc = L.serl_rollout(*args, stream)
-    else:      # evaluation mode (envs/phlabenv.py:295-301): longer episodes, wider reference transitions
-        rc = L.serl_rollout_eval(*args, ctypes.c_double(t_max), ctypes.c_double(smooth_width if smooth_width is not None else float(t_max // 6)), stream)
-    _native.check(rc, 'serl_rollout')
+    p = lambda t: t.data_ptr() if t is not None else None
+    d = _native.RolloutDesc()
+    d.d_weights, d.pop, d.shape = p(weights), pop, shape
+    d.d_ref_levels, d.d_ref_starts, d.d_env_mode, d.n_envs, d.horizon = p(ref_levels), p(ref_starts), p(env_mode), n_envs, horizon
+    d.d_action_noise = p(action_noise)
+    d.d_returns, d.d_steps, d.d_fitness, d.d_trace, d.d_actions = p(r.returns), p(r.steps), p(r.fitness), p(r.trace), p(getattr(r, 'actions', None))
+    if t_max is not None:      # evaluation mode (envs/phlabenv.py:295-301): longer episodes, wider reference transitions
+        d.t_max = float(t_max)
+        d.smooth_width = float(smooth_width if smooth_width is not None else float(t_max // 6))
+    d.d_env_order = p(env_order)
+    d.d_replay, d.replay_env = p(getattr(r, 'replay', None)), int(replay_env if replay_env is not None else 0)
+    d.d_status = p(getattr(r, 'status', None))
+    _native.check(L.serl_rollout_run(ctypes.byref(d), stream), 'serl_rollout_run')
     return r
+
+
+def actor_forward(genome, shape, obs):
+    """Actor.forward for a batch (base/core/genetic_agent.py:104-109): genome [P] fp32 cuda, obs [n,7] fp32 cuda -> [n,3].
+    Same device code (summation order, activations) as the rollout kernel."""
+    if not genome.is_cuda:
+        raise _native.NativeError('actor_forward needs CUDA tensors (no CPU fallback)')
+    assert genome.dtype == torch.float32 and genome.is_contiguous() and genome.numel() == num_params(shape)
+    assert obs.dtype == torch.float32 and obs.is_contiguous() and obs.shape[1] == shape.state_dim
+    out = torch.empty((obs.shape[0], shape.action_dim), dtype=torch.float32, device=genome.device)
+    stream = ctypes.c_void_p(torch.cuda.current_stream(genome.device).cuda_stream)
+    _native.check(_native.lib().serl_actor_forward(_ptr(genome), ctypes.byref(shape), _ptr(obs), obs.shape[0], _ptr(out), stream),
+                  'serl_actor_forward')
+    return out
 
 
 def smoothness(actions, steps, dt=0.01):

@@ -30,6 +30,7 @@ typedef %(real)s real;
 #define PLANT_IC(v) static const double plant_ic_unused_##v[19]
 #define PLANT_PV_TABLE static const real plant_pv[6][PLANT_NPV]
 #define PLANT_PV(k) plant_pvrow[k]
+#define PLANT_XI(i) (i)
 #define PLANT_DIV(a, b) ((a) / (b))
 #define PLANT_SQRT sqrt%(sfx)s
 #define PLANT_FABS fabs%(sfx)s
@@ -46,14 +47,12 @@ typedef %(real)s real;
 #include "%(gen)s/plant_consts.h"
 #include "%(gen)s/plant_ic.h"
 #include "%(gen)s/plant_rhs_common.h"
-#include "%(gen)s/plant_rhs_ice.h"
 #include "%(gen)s/plant_rhs_nav.h"
 void dev_rhs(int variant, const double* Xd, const double* Ud, double* out) {
     real X[19], U[3], xdot[19], nav[19];
     for (int i = 0; i < 19; ++i) { X[i] = (real)Xd[i]; xdot[i] = 0; }
     for (int i = 0; i < 3; ++i) U[i] = (real)Ud[i];
-    if (variant == 1) plant_rhs_ice(X, U, xdot, plant_tables_blob);
-    else plant_rhs_common(X, U, xdot, plant_tables_blob, plant_pv[variant]);
+    plant_rhs_common(X, U, xdot, plant_tables_blob, plant_pv[variant]);      /* one function for every variant */
     plant_rhs_nav(X, U, nav, plant_tables_blob);
     xdot[8] = nav[8]; xdot[10] = nav[10]; xdot[11] = nav[11];
     for (int i = 0; i < 19; ++i) out[i] = (double)xdot[i];
