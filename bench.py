@@ -161,10 +161,76 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ our arm
+CFG4_MODES = ['nominal', 'be', 'jr', 'sa', 'se', 'ice', 'cg']        # BASELINE config 4: fault / plant mode randomised per env
+
+
+def mixed_modes(n_envs, seed=7):
+    rs = np.random.RandomState(seed)
+    return [CFG4_MODES[i] for i in rs.randint(0, len(CFG4_MODES), n_envs)]
+
+
+def timed_region(step_fn, steps, warmup, flush, sync_all):
+    """W warm-up steps, then exactly K steps bracketed by barrier + synchronize; CUDA events on the launching stream.
+    Returns (elapsed ms of the K steps, mean per-step kernel ms, last result)."""
+    import torch
+    res = None
+    for _ in range(warmup):
+        flush.zero_()
+        res = step_fn(res)
+    sync_all()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    t_begin.record()
+    for i in range(steps):
+        flush.zero_()
+        ev[i][0].record()
+        res = step_fn(res)
+        ev[i][1].record()
+    t_end.record()
+    sync_all()
+    return t_begin.elapsed_time(t_end), float(np.mean([a.elapsed_time(b) for a, b in ev])), res
+
+
+def agent_train_timing(dev, pop, n_envs, generations=3):
+    """One generation through the public API (Agent.train, base/core/agent.py:211-315 mirror) at the bench configuration,
+    EA loop only (-test_ea: no TD3 gradient steps; the RL exploration + validation episodes still fly), wall clock."""
+    import random
+    import types
+    import torch
+    from serl_b200.core import agent as agent_mod
+    from serl_b200.envs import config as env_config
+    from serl_b200.parameters import Parameters
+    cla = types.SimpleNamespace(env='PHlab_attitude_nominal', pop_size=pop, test_ea=True, num_envs=n_envs, seed=7, mut_type='normal',
+                                should_log=False, frames=10 ** 9)
+    cwd = os.getcwd()
+    os.chdir('/tmp')
+    try:
+        args = Parameters(cla)
+    finally:
+        os.chdir(cwd)
+    env = env_config.select_env(args.env_name)
+    args.action_dim, args.state_dim = env.action_space.shape[0], env.observation_space.shape[0]
+    torch.manual_seed(7); np.random.seed(7); random.seed(7)
+    env.seed(7)
+    ag = agent_mod.Agent(args, env)
+    ag.pop.genomes.copy_(torch.from_numpy(population(pop)).to(dev))
+    times, stats = [], None
+    for g in range(generations + 1):
+        ag.pop.genomes.copy_(torch.from_numpy(population(pop)).to(dev))       # keep flying full episodes: a trained population
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        stats = ag.train()
+        torch.cuda.synchronize()
+        if g > 0:
+            times.append(1e3 * (time.perf_counter() - t0))
+    return float(np.mean(times)), stats, ag
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from serl_b200 import rollout, _native
+    from serl_b200 import rollout, _native, engine
     from serl_b200 import refsig
     if not os.path.exists(_native.LIB_PATH):      # normally prebuilt in-tree; build the CUDA extension if it is not there
         if int(os.environ.get('LOCAL_RANK', '0')) == 0:
@@ -185,81 +251,80 @@ def run_ours(args):
     dev = torch.device('cuda', local)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
+    strong = args.scaling == 'strong'
 
     sh = rollout.actor_shape(HIDDEN, 3, 'tanh')
-    w_host = torch.from_numpy(population(POP, seed=7 + rank)).pin_memory()
     lv_np, st_np = refsig.make_ref_params(N_ENVS)
     lv_host = torch.from_numpy(lv_np).pin_memory()
     st_host = torch.from_numpy(st_np).pin_memory()
-    md_host = torch.full((N_ENVS,), rollout.mode_code('nominal'), dtype=torch.int32).pin_memory()
-    w = w_host.to(dev)
-    lv, st, md = lv_host.to(dev), st_host.to(dev), md_host.to(dev)
-    fit_all = torch.empty((world * POP,), dtype=torch.float64, device=dev)
+    nominal = torch.full((N_ENVS,), rollout.mode_code('nominal'), dtype=torch.int32)
+    mixed = torch.tensor([rollout.mode_code(m) for m in mixed_modes(N_ENVS)], dtype=torch.int32)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)      # > 126 MB L2
-
-    def one_step(res=None):
-        r = rollout.population_rollout(w, sh, lv, st, md, horizon=HORIZON, out=res)
-        if world > 1:
-            dist.all_gather_into_tensor(fit_all, r.fitness)
-        else:
-            fit_all.copy_(r.fitness)
-        return r
 
     def sync_all():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    res = None
-    for _ in range(args.warmup):
-        flush.zero_()
-        res = one_step(res)
-    sync_all()
+    def make_workload(pop_total_or_local, modes_host, shard):
+        """device tensors of one workload: weak = `POP` actors per rank (rank-specific population), strong / config 4 = ONE
+        population of POP actors, identical on every rank, each rank flies its contiguous shard."""
+        if shard:
+            w_all = population(POP, seed=7)
+            lo, hi = engine.shard_bounds(POP, world, rank)
+            w_host = torch.from_numpy(np.ascontiguousarray(w_all[lo:hi])).pin_memory()
+        else:
+            w_host = torch.from_numpy(population(POP, seed=7 + rank)).pin_memory()
+        md_host = modes_host.pin_memory()
+        return {'w_host': w_host, 'md_host': md_host, 'w': w_host.to(dev), 'lv': lv_host.to(dev), 'st': st_host.to(dev),
+                'md': md_host.to(dev), 'order': rollout.variant_sorted_order(md_host.to(dev)), 'pop_total': POP if shard else POP * world}
+
+    def make_step(wl):
+        fit_all = torch.empty((wl['pop_total'],), dtype=torch.float64, device=dev)
+
+        def one_step(res=None):
+            r = rollout.population_rollout(wl['w'], sh, wl['lv'], wl['st'], wl['md'], horizon=HORIZON, out=res, env_order=wl['order'])
+            fit_all.copy_(engine.gather_fitness(r.fitness, wl['pop_total'], world, rank))     # THE collective of the path
+            return r
+        return one_step
+
+    def measure(wl, steps, warmup):
+        elapsed_ms, kern_ms, res = timed_region(make_step(wl), steps, warmup, flush, sync_all)
+        local_steps = int(res.steps.sum().item())
+        res.check()
+        stats = torch.tensor([elapsed_ms, kern_ms], dtype=torch.float64, device=dev)
+        tot = torch.tensor([float(local_steps)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+            dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        elapsed_ms, kern_ms = stats.tolist()
+        return {'elapsed_ms': elapsed_ms, 'kern_ms': kern_ms, 'total_steps': tot.item(), 'value': tot.item() * steps / (elapsed_ms * 1e-3),
+                'res': res}
+
+    # ---- headline: weak scaling = BASELINE config 3 per GPU; strong = BASELINE config 4 (one pop = 512, mixed faults) sharded
+    wl = make_workload(POP, mixed if strong else nominal, shard=strong)
     launches0 = _native.lib().serl_launch_count()
     sampler = ClockSampler(local) if rank == 0 else None
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    t_begin = torch.cuda.Event(enable_timing=True)
-    t_end = torch.cuda.Event(enable_timing=True)
-    sync_all()
-    t_begin.record()
-    for i in range(args.steps):
-        flush.zero_()
-        ev[i][0].record()
-        res = one_step(res)
-        ev[i][1].record()
-    t_end.record()
-    sync_all()
+    m = measure(wl, args.steps, args.warmup)
     clocks = sampler.stop() if sampler else None
-    launches = _native.lib().serl_launch_count() - launches0
-    elapsed_ms = t_begin.elapsed_time(t_end)
-    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
-    local_steps = int(res.steps.sum().item())
-    stats = torch.tensor([elapsed_ms, kern_ms], dtype=torch.float64, device=dev)
-    tot = torch.tensor([float(local_steps)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    elapsed_ms, kern_ms = stats.tolist()
-    total_steps = tot.item()
-    value = total_steps * args.steps / (elapsed_ms * 1e-3)
+    launches = (_native.lib().serl_launch_count() - launches0) // (args.steps + args.warmup) * args.steps
+    res = m['res']
 
     # ---- end to end through the public API with host buffers (H2D genomes + env params, D2H fitness) every step
-    fit_host = torch.empty((POP,), dtype=torch.float64).pin_memory()
-    h2d = w_host.numel() * 4 + lv_host.numel() * 8 + st_host.numel() * 8 + md_host.numel() * 4
+    pop_local = wl['w'].shape[0]
+    fit_host = torch.empty((wl['pop_total'],), dtype=torch.float64).pin_memory()
+    h2d = wl['w_host'].numel() * 4 + lv_host.numel() * 8 + st_host.numel() * 8 + wl['md_host'].numel() * 4
     d2h = fit_host.numel() * 8
 
-    from serl_b200 import engine
-
     def e2e_step(res):
-        # the call a user makes: host genomes + env parameters in, fitness out (engine.evaluate_population is what
-        # Agent.train uses); H2D of this rank's inputs and D2H of the gathered fitness are inside the timed region
-        w.copy_(w_host, non_blocking=True)
-        lv.copy_(lv_host, non_blocking=True)
-        st.copy_(st_host, non_blocking=True)
-        md.copy_(md_host, non_blocking=True)
-        r = rollout.population_rollout(w, sh, lv, st, md, horizon=HORIZON, out=res)
-        fit = engine.gather_fitness(r.fitness, world * POP, world, rank) if world > 1 else r.fitness
-        fit_host.copy_(fit[rank * POP:(rank + 1) * POP], non_blocking=True)
+        # the call a user makes: host genomes + env parameters in, fitness out; H2D of this rank's inputs and D2H of the
+        # gathered fitness are inside the timed region
+        wl['w'].copy_(wl['w_host'], non_blocking=True)
+        wl['lv'].copy_(lv_host, non_blocking=True)
+        wl['st'].copy_(st_host, non_blocking=True)
+        wl['md'].copy_(wl['md_host'], non_blocking=True)
+        r = rollout.population_rollout(wl['w'], sh, wl['lv'], wl['st'], wl['md'], horizon=HORIZON, out=res, env_order=wl['order'])
+        fit_host.copy_(engine.gather_fitness(r.fitness, wl['pop_total'], world, rank), non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return r
 
@@ -275,45 +340,57 @@ def run_ours(args):
     e2e_ms = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    e2e_value = total_steps * n_e2e / (e2e_ms.item() * 1e-3)
+    e2e_value = m['total_steps'] * n_e2e / (e2e_ms.item() * 1e-3)
 
-    # ---- one full generation (rollout + SSNE.epoch: K2 select, host RNG planner, K3-K5), informative, rank-local
-    gen_ms = None
-    epoch_timing = None
-    smooth_timing = None
+    # ---- the other scaling mode as a second, shorter measurement (same barrier / max-over-ranks timing)
+    other = None
+    if not args.no_generation:
+        wl2 = make_workload(POP, nominal if strong else mixed, shard=not strong)
+        m2 = measure(wl2, 2, 1)
+        other = {'scaling': 'weak' if strong else 'strong',
+                 'workload': ('BASELINE config 3 per GPU (pop=512/GPU, nominal)' if strong else
+                              'BASELINE config 4: ONE population of 512 actors sharded over the GPUs, fault/plant mode per env uniform over '
+                              '{nominal,be,jr,sa,se,ice,cg}, identical population on every rank'),
+                 'value': m2['value'], 'unit': 'env-steps/s', 'ms_per_step': m2['elapsed_ms'] / 2, 'executed_steps_per_step': m2['total_steps'],
+                 'note': 'strong scaling is bounded by the serial latency of one 2001-step trajectory (about 0.15 s for a warp alone on an '
+                         'SM): with 64 actors x 4 warps per GPU the SMs hold 2 resident warps instead of 8'}
+        del wl2, m2
+
+    # ---- one full generation (rollout + SSNE.epoch: K2 select, host RNG planner, K3-K5), rank-local, and Agent.train()
+    gen_ms = epoch_timing = smooth_timing = extras = agent_line = None
     if world == 1 and not args.no_generation:
         import random
         from serl_b200 import evo
         np.random.seed(7); random.seed(7)
+        w = wl['w'].clone()
         times = []
         for _ in range(2):
             g0 = torch.cuda.Event(enable_timing=True); g1 = torch.cuda.Event(enable_timing=True)
             g0.record()
-            r = rollout.population_rollout(w, sh, lv, st, md, horizon=HORIZON, out=res)
+            r = rollout.population_rollout(w, sh, wl['lv'], wl['st'], wl['md'], horizon=HORIZON, out=res)
             _, plan = evo.epoch_flat(w, r.fitness, (7, 3, HIDDEN, 3))
             epoch_timing = plan.timing
             g1.record(); torch.cuda.synchronize()
             times.append(g0.elapsed_time(g1))
         gen_ms = float(np.mean(times))
-        # the same with the action-smoothness metric of every episode (K6; agent.py:128-134, -smooth_fitness)
+        # the action-smoothness metric of every episode (K6; agent.py:128-134, -smooth_fitness)
         s0 = torch.cuda.Event(enable_timing=True); s1 = torch.cuda.Event(enable_timing=True); s2 = torch.cuda.Event(enable_timing=True)
         s0.record()
-        r = rollout.population_rollout(w, sh, lv, st, md, horizon=HORIZON, actions=True)
+        r = rollout.population_rollout(wl['w'], sh, wl['lv'], wl['st'], wl['md'], horizon=HORIZON, actions=True)
         s1.record()
         sm = rollout.smoothness(r.actions, r.steps)
         s2.record(); torch.cuda.synchronize()
         smooth_timing = {'rollout_with_action_history_ms': s0.elapsed_time(s1), 'smoothness_kernel_ms': s1.elapsed_time(s2),
                          'action_history_bytes': int(r.actions.numel() * 4)}
-        del r, sm
-        launches_note = 'rollout + fitness_mean per step; a generation adds K2 + K3..K5 launches'
+        del r, sm, w
 
-    extras = None
-    if world == 1 and not args.no_generation:
-        def timed_rollout(genomes, modes_t):
+        def timed_rollout(genomes, modes_t, n_envs=N_ENVS, lvx=None, stx=None):
             a0 = torch.cuda.Event(enable_timing=True); a1 = torch.cuda.Event(enable_timing=True)
-            rollout.population_rollout(genomes, sh, lv, st, modes_t, horizon=HORIZON)       # warm
+            lvx = wl['lv'] if lvx is None else lvx
+            stx = wl['st'] if stx is None else stx
+            rollout.population_rollout(genomes, sh, lvx, stx, modes_t, horizon=HORIZON)       # warm
             a0.record()
-            rr = rollout.population_rollout(genomes, sh, lv, st, modes_t, horizon=HORIZON)
+            rr = rollout.population_rollout(genomes, sh, lvx, stx, modes_t, horizon=HORIZON)
             a1.record(); torch.cuda.synchronize()
             n = int(rr.steps.sum().item())
             return {'executed_env_steps': n, 'ms': a0.elapsed_time(a1), 'env_steps_per_sec': n / (a0.elapsed_time(a1) * 1e-3),
@@ -324,36 +401,53 @@ def run_ours(args):
         torch.manual_seed(7)
         a_ns = types.SimpleNamespace(hidden_size=HIDDEN, num_layers=3, activation_actor='tanh', state_dim=7, action_dim=3)
         w0 = torch.stack([genetic_agent.Actor(a_ns).flat() for _ in range(POP)]).to(dev)
-        extras = {'random_init_population': timed_rollout(w0, md)}
-        # (ii) BASELINE config 4 style: fault / plant mode randomised per env over {nominal, be, jr, sa, se, ice, cg}
-        mrng = np.random.RandomState(7)
-        mixed = [['nominal', 'be', 'jr', 'sa', 'se', 'ice', 'cg'][i] for i in mrng.randint(0, 7, N_ENVS)]
-        md_mixed = torch.tensor([rollout.mode_code(m) for m in mixed], dtype=torch.int32, device=dev)
-        extras['mixed_faults_per_env'] = timed_rollout(w, md_mixed)
+        extras = {'random_init_population': timed_rollout(w0, wl['md'])}
+        # (ii) BASELINE config 2: pop = 50 (SERL50), 64 envs
+        lv2, st2 = refsig.make_ref_params(64)
+        extras['config2_pop50_64envs'] = timed_rollout(torch.from_numpy(population(50)).to(dev), wl['md'][:64].contiguous(), 64,
+                                                       torch.as_tensor(lv2, device=dev), torch.as_tensor(st2, device=dev))
+        # (iii) per-GPU share of config 4 on 8 GPUs: 64 actors x 128 envs
+        extras['pop64_128envs'] = timed_rollout(wl['w'][:64].contiguous(), wl['md'])
+        # ---- the public API: Agent.train() generations at the bench configuration
+        if not args.no_agent:
+            ag_ms, ag_stats, ag = agent_train_timing(dev, POP, N_ENVS)
+            agent_line = {'generation_ms': ag_ms, 'population_rollout_ms': m['kern_ms'], 'ratio_to_population_rollout': ag_ms / m['kern_ms'],
+                          'what': 'wall clock of Agent.train() (EA loop, -test_ea): RL exploration + RL validation episodes on a side '
+                                  'stream, population x (128 + 5 validation) envs in one launch, SSNE.epoch (K2-K5 + host planner), stats',
+                          'frames_per_generation': int(ag.gen_frames), 'test_score': float(ag_stats['test_score'])}
+            del ag
 
     if rank == 0:
         peak, how = peaks()
         traffic = None
-        tpath = os.path.join(ROOT, 'profiles', 'r01_rollout_traffic.json')
-        if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get('dram_bytes_per_launch')
-        per_gpu_steps = total_steps / world
+        for name in ('r02_rollout_traffic.json', 'r01_rollout_traffic.json'):
+            tpath = os.path.join(ROOT, 'profiles', name)
+            if os.path.exists(tpath):
+                traffic = json.load(open(tpath)).get('dram_bytes_per_launch')
+                break
+        per_gpu_steps = m['total_steps'] / world
+        kern_ms = m['kern_ms']
         achieved = BYTES_PER_STEP * per_gpu_steps / (kern_ms * 1e-3) / 1e9
+        workload = ('BASELINE config 4: PH-LAB mixed faults per env, ONE pop=512 sharded over %d GPU(s), 128 envs, 2001-step horizon, h=72 L=3 tanh'
+                    % world if strong else
+                    'BASELINE config 3: PH-LAB nominal h2000_v90, pop=512/GPU, 128 envs, 2001-step horizon, actor h=72 L=3 tanh')
         line = {
-            'metric': 'env_steps_per_sec', 'value': value, 'unit': 'env-steps/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-            'ms_per_step': elapsed_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'metric': 'env_steps_per_sec', 'value': m['value'], 'unit': 'env-steps/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': m['elapsed_ms'] / args.steps, 'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None,
             'dtype': 'f64 plant + f32 actor', 'data': 'synthetic',
-            'config': {'workload': 'PH-LAB nominal h2000_v90, pop=512/GPU, 128 envs, 2001-step horizon, actor h=72 L=3 tanh; '
-                                   'SERL10 checkpoint tiled + N(0,1e-3) noise; executed steps counted by the kernel',
-                       'pop_per_gpu': POP, 'n_envs': N_ENVS, 'horizon': HORIZON, 'hidden': HIDDEN,
-                       'executed_steps_per_step': total_steps, 'l2': 'flushed between timed iterations (256 MiB memset)',
-                       'parallelism': 'population sharded over %d GPU(s), NCCL all-gather of fitness' % world},
+            'config': {'workload': workload + '; SERL10 checkpoint tiled + N(0,1e-3) noise; executed steps counted by the kernel',
+                       'pop_per_gpu': pop_local, 'pop_total': wl['pop_total'], 'n_envs': N_ENVS, 'horizon': HORIZON, 'hidden': HIDDEN,
+                       'executed_steps_per_step': m['total_steps'], 'l2': 'flushed between timed iterations (256 MiB memset)',
+                       'parallelism': 'population sharded over %d GPU(s), one NCCL all-gather of fitness per step' % world},
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
             'gpu_launches': int(launches),
-            'generation_ms': gen_ms, 'epoch_breakdown': (epoch_timing if gen_ms is not None else None), 'smoothness': smooth_timing, 'other_workloads': extras,
+            'gpu_launches_per_step': 'genome_layout (K0) + rollout_kernel_persist (K1) + fitness_mean',
+            'other_scaling_mode': other,
+            'generation_ms': gen_ms, 'epoch_breakdown': (epoch_timing if gen_ms is not None else None), 'agent_train': agent_line,
+            'smoothness': smooth_timing, 'other_workloads': extras,
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
-                         'peak_source': how, 'kernel': 'rollout_kernel', 'kernel_ms': kern_ms,
+                         'peak_source': how, 'kernel': 'rollout_kernel_persist', 'kernel_ms': kern_ms,
                          'note': 'BASELINE metric denominator (208 B/env-step state round-trip model); the kernel keeps state on chip and is '
                                  'bound by fp64/fp32 issue, see fp_issue',
                          'fp_issue': {'f64_gflops': FLOP_PER_STEP_F64 * per_gpu_steps / (kern_ms * 1e-3) / 1e9,
@@ -385,7 +479,10 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
-    ap.add_argument('--no-generation', action='store_true', help='skip the rollout+epoch generation timing')
+    ap.add_argument('--no-generation', action='store_true', help='skip the rollout+epoch generation timing and the other-workload legs')
+    ap.add_argument('--no-agent', action='store_true', help='skip the Agent.train() timing')
+    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
+                    help='weak: BASELINE config 3 per GPU (pop=512/GPU); strong: BASELINE config 4 (ONE pop=512, mixed faults, sharded)')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -91,6 +91,8 @@ int serl_rollout_eval(const float* d_weights, int32_t pop, const serl_actor_shap
  *                envs/phlabenv.py:369-375 -> critical buffer); rows past the episode's length are not written
  *   d_status     optional int32 word the kernel ORs error bits into (SERL_STATUS_*); the caller zeroes it and reads it
  *                after synchronising
+ *   sm_limit     > 0: use at most that many SMs (CTAs of the persistent kernel) — leaves room for small launches that run
+ *                concurrently on other streams (the RL / validation episodes of Agent.train); 0 = all SMs
  * t_max <= 0 selects the training defaults (20 s, smooth width 3 s). */
 #define SERL_REPLAY_COLS 20
 enum { SERL_STATUS_NONFINITE = 1 };   /* a trajectory's state / return became NaN or infinite */
@@ -103,6 +105,7 @@ typedef struct {
     const int32_t* d_env_order;
     float* d_replay; int32_t replay_env;
     int32_t* d_status;
+    int32_t sm_limit;
 } serl_rollout_desc;
 int serl_rollout_run(const serl_rollout_desc* desc, void* stream);
 

@@ -22,7 +22,7 @@ class RolloutDesc(ctypes.Structure):
                 ('d_trace', ctypes.c_void_p), ('d_actions', ctypes.c_void_p),
                 ('t_max', ctypes.c_double), ('smooth_width', ctypes.c_double),
                 ('d_env_order', ctypes.c_void_p), ('d_replay', ctypes.c_void_p), ('replay_env', ctypes.c_int32),
-                ('d_status', ctypes.c_void_p)]
+                ('d_status', ctypes.c_void_p), ('sm_limit', ctypes.c_int32)]
 
 
 REPLAY_COLS = 20

@@ -1,16 +1,23 @@
 """Mirror of base/core/agent.py (Agent :13-352): same constructor, evaluate(), train(), validate_agent(), save_agent() and
 stats keys, with the per-generation fitness hot path on the GPU:
 
-  * the population loop `for net in pop: for i in range(num_evals): evaluate(net)` (:234-241) is ONE fused rollout launch
-    over pop x num_envs trajectories (serl_b200/rollout.py, csrc/rollout.cu), sharded over ranks when torch.distributed
-    is initialised (serl_b200/engine.py);
-  * single episodes (`evaluate`, used for the champion / RL validation and the RL exploration episode) run the same
-    kernel with a per-step trace, from which the Episode record and the replay transitions are rebuilt;
+  * the population loop `for net in pop: for i in range(num_evals): evaluate(net)` (:234-241) AND the champion's
+    validation episodes (:255-258) are ONE fused rollout launch over pop x (num_envs + 5) trajectories
+    (serl_b200/rollout.py, csrc/rollout.cu), sharded over ranks when torch.distributed is initialised
+    (serl_b200/engine.py): every actor also flies the 5 validation references (+4 % work), the champion's row is read
+    once the ranking is known — no serial 150 ms single-trajectory launch after the rollout;
+  * the transitions of the stored evaluation (:101-112, `store_transition=(i == num_evals-1)`) are written by the kernel
+    (K1 replay rows) and appended on the device to the shared replay buffer and the per-actor buffers — no traced
+    re-flight, no per-actor host loop;
+  * the RL exploration episode (:267-268) — and, when no gradient step can change the RL actor this generation
+    (`frac_frames_train == 0`, i.e. -test_ea), the RL validation episodes (:273-275) — are launched on a side stream BEFORE
+    the population kernel, which leaves them two SMs (`sm_limit`), so they cost no wall-clock time;
   * `self.evolver.epoch` runs on the device-resident genomes (core/mod_neuro_evo.py -> serl_b200/evo.py).
 
 Documented deviations from the reference: the conditions at agent.py:45,228 are read as intended
 (`if self.pop`), save_agent's `isEmpty()` works; all actors of a generation see the SAME num_envs reference signals (fair
-ranking) instead of an independent draw per episode; every trajectory starts from a fresh env (zero stale error).
+ranking) instead of an independent draw per episode; every trajectory starts from a fresh env (zero stale error); TD3 samples
+its batches with a device generator instead of stdlib `random` (so the SSNE planner's stream does not depend on buffer sizes).
 """
 import os
 from typing import Dict
@@ -25,6 +32,11 @@ from .. import engine, refsig, rollout
 from ..population import PopulationList
 
 
+class _Flight:
+    """an asynchronous launch of n episodes of ONE actor (result tensors stay on the device until collected)."""
+    __slots__ = ('r', 'levels', 'starts', 'n', 'noise_state', 'stream', 'event')
+
+
 class Agent:
     def __init__(self, args, environment):
         self.args = args
@@ -35,7 +47,7 @@ class Agent:
         self.device = torch.device('cuda', torch.cuda.current_device())
         self.pop = PopulationList(args, self.device) if args.pop_size else []
         self.rl_agent = td3.TD3(args)
-        self.replay_buffer = replay_memory.ReplayMemory(args.buffer_size, args.device)
+        self.replay_buffer = replay_memory.DeviceReplayMemory(args.buffer_size, self.device, seed=int(getattr(args, 'seed', 7)))
         self.noise_process = mod_utils.GaussianNoise(args.action_dim, sd=args.noise_sd)
         if len(self.pop):
             self.evolver = utils_ne.SSNE(self.args, self.rl_agent.critic, self.evaluate)
@@ -50,7 +62,9 @@ class Agent:
         self.champion = None
         self.champion_actor = None
         self.champion_history = None
-        self.store_population_transitions = args.frac_frames_train > 0
+        self.store_population_transitions = args.frac_frames_train > 0 or getattr(args, 'mut_type', 'normal') in ('proximal', 'safe')
+        self._side = torch.cuda.Stream(self.device, priority=-1)
+        self.timing = {}
 
     # ------------------------------------------------------------------------------------------------ episodes
     def _genome_of(self, agent):
@@ -65,66 +79,96 @@ class Agent:
             t += self.env.dt
         return t
 
-    def _episode_from_trace(self, agent, tr, n, x_ic, store_transition, refs):
-        rewards = [float(r) for r in tr[:n, 15]]
-        actions = tr[:n, 12:15].copy()
+    def _horizon(self):
+        return int(round(self.env.t_max / self.env.dt)) + 1
+
+    def _eval_kw(self):
+        env = self.env
+        return {} if env.t_max == 20 else {'t_max': float(env.t_max), 'smooth_width': refsig.widths(env.t_max)[1]}
+
+    def _fly(self, agent, n, is_action_noise=False, store_transition=False, trace=False, stream=None) -> _Flight:
+        """launch n episodes of one actor (fresh reference signals each) without waiting for them."""
+        env = self.env
+        draws = [env.draw_reference() for _ in range(n)]
+        f = _Flight()
+        f.levels, f.starts, f.n = [d[0] for d in draws], [d[1] for d in draws], n
+        f.noise_state = None
+        horizon = self._horizon()
+        noise_host = None
+        if is_action_noise:
+            # one np.random.randn(3) per executed step (agent.py:90-93): draw a full horizon, rewind the global stream to
+            # "exactly the steps that ran" once the episode length is known (collect)
+            assert n == 1
+            f.noise_state = np.random.get_state()
+            z = np.random.randn(horizon, 3)
+            noise_host = np.clip(self.args.noise_sd * z, -self.args.noise_clip, self.args.noise_clip).astype(np.float32).reshape(1, 1, -1, 3)
+        genome = self._genome_of(agent)
+        f.stream = stream
+        ctx = torch.cuda.stream(stream) if stream is not None else _null()
+        if stream is not None:
+            stream.wait_stream(torch.cuda.current_stream(self.device))        # genomes / weights written on the main stream
+        with ctx:
+            lv = torch.as_tensor(np.stack(f.levels), device=self.device)
+            st = torch.as_tensor(np.stack(f.starts), device=self.device)
+            md = torch.full((n,), env.mode_code, dtype=torch.int32, device=self.device)
+            noise = torch.as_tensor(noise_host, device=self.device) if noise_host is not None else None
+            f.r = rollout.population_rollout(genome, self.shape, lv, st, md, trace=trace, action_noise=noise, horizon=horizon,
+                                             actions=True, replay_env=0 if store_transition else None, **self._eval_kw())
+            f.r.smoothness = rollout.smoothness(f.r.actions, f.r.steps)
+            f.event = torch.cuda.Event()
+            f.event.record()
+        return f
+
+    def _store_rows(self, agent, rows, n):
+        """append the n transitions of one stored episode (device rows) to the shared and the agent's own buffers."""
+        rows = rows[:n]
+        self.replay_buffer.add_rows(rows)
+        agent.buffer.add_rows(rows)
+        crit = rows[rows[:, 19] > 0.5]
+        if crit.shape[0]:
+            agent.critical_buffer.add_rows(crit)
+        self.num_frames += n
+        self.gen_frames += n
+        self.num_episodes += 1
+
+    def _collect(self, agent, f: _Flight, store_transition=False, want_history=False):
+        """wait for a flight and rebuild the reference's per-episode records: list of Episode."""
+        f.event.synchronize()
+        f.r.check()
+        steps = f.r.steps[0].cpu().numpy()
+        returns = f.r.returns[0].cpu().numpy()
+        sm = f.r.smoothness[0].cpu().numpy()
+        if f.noise_state is not None:
+            np.random.set_state(f.noise_state)
+            np.random.randn(int(steps[0]), 3)
         if store_transition:
-            # transitions (obs, action, next_obs, reward, done) of agent.py:101-112, rebuilt from the trace in one shot
-            x = tr[:n, 0:12]
-            next_obs = np.hstack((tr[:n, 19:22], x[:, [0, 1, 2, 4]]))
-            obs = np.vstack((np.hstack((np.zeros(3), x_ic[[0, 1, 2, 4]]))[None], next_obs[:-1]))
-            done = np.zeros(n); done[-1] = 1.0
-            rew = np.asarray(rewards)
-            batch = (obs, tr[:n, 16:19], next_obs, rew, done)
-            self.replay_buffer.add_batch(*batch)
-            agent.buffer.add_batch(*batch)
-            # get_cost (phlabenv.py:369-375, incl. its degrees-vs-radians comparison on the bank angle)
-            cost = (np.rad2deg(np.abs(x[:, 4])) > 11.0) | (np.rad2deg(np.abs(x[:, 6])) > 0.75 * self.env.max_phi) | (x[:, 3] < x_ic[3] / 3)
-            if cost.any():
-                agent.critical_buffer.add_batch(*(b[cost] for b in batch))
-            self.num_frames += n
-            self.gen_frames += n
-            self.num_episodes += 1
-            state_lst = []
-        else:
-            state_lst = [tr[k, 0:12].copy() for k in range(n)]
-        smoothness = calc_smoothness(actions, plot_spectra=False)
-        fitness = np.sum(rewards)
-        if self.args.smooth_fitness:
-            fitness += smoothness
-        return Episode(fitness=fitness, smoothness=smoothness, length=self._final_time(n), state_history=state_lst,
-                       ref_signals=refs, actions=actions, reward_lst=rewards)
+            self._store_rows(agent, f.r.replay[0], int(steps[0]))
+        env = self.env
+        theta_trim = np.rad2deg(self._initial_state(env)[7])
+        from ..envs.phlabenv import _RefSignal
+        sw = refsig.widths(env.t_max)[1]
+        eps = []
+        for e in range(f.n):
+            n = int(steps[e])
+            refs = [_RefSignal(f.levels[e][0], f.starts[e][0], theta_trim, sw, env.t_max), _RefSignal(f.levels[e][1], f.starts[e][1], 0.0, sw), lambda t: 0.0]
+            fitness = float(returns[e]) + (float(sm[e]) if self.args.smooth_fitness else 0.0)
+            state_lst, actions, rewards = [], None, None
+            if f.r.trace is not None and (want_history or f.n == 1):
+                tr = f.r.trace[0, e, :n].cpu().numpy()
+                rewards = [float(x) for x in tr[:, 15]]
+                actions = tr[:, 12:15].copy()
+                state_lst = [] if store_transition else [tr[k, 0:12].copy() for k in range(n)]
+            else:
+                actions = f.r.actions[0, e, :n].cpu().numpy().astype(np.float64) if want_history else np.zeros((0, 3))
+                rewards = _ReturnOnly(float(returns[e]))
+            eps.append(Episode(fitness=fitness, smoothness=float(sm[e]), length=self._final_time(n), state_history=state_lst,
+                               ref_signals=refs, actions=actions, reward_lst=rewards))
+        return eps
 
     def evaluate(self, agent, is_action_noise: bool, store_transition: bool) -> Episode:
         """Play one episode (agent.py:63-138) on the GPU."""
-        env = self.env
-        levels, starts = env.draw_reference()
-        lv = torch.as_tensor(levels[None], device=self.device)
-        st = torch.as_tensor(starts[None], device=self.device)
-        md = torch.tensor([env.mode_code], dtype=torch.int32, device=self.device)
-        noise = None
-        if is_action_noise:
-            # one np.random.randn(3) per executed step (agent.py:90-93): draw a full horizon, then rewind the global
-            # stream to "exactly the steps that ran" once the episode length is known
-            state = np.random.get_state()
-            z = np.random.randn(int(round(env.t_max / env.dt)) + 1, 3)
-            clipped = np.clip(self.args.noise_sd * z, -self.args.noise_clip, self.args.noise_clip)
-            noise = torch.as_tensor(clipped.astype(np.float32).reshape(1, 1, -1, 3), device=self.device)
-        horizon = int(round(env.t_max / env.dt)) + 1
-        kw = {} if env.t_max == 20 else {'t_max': float(env.t_max), 'smooth_width': refsig.widths(env.t_max)[1]}
-        r = rollout.population_rollout(self._genome_of(agent), self.shape, lv, st, md, trace=True, action_noise=noise,
-                                       horizon=horizon, **kw)
-        n = int(r.steps[0, 0].item())
-        tr = r.trace[0, 0, :n].cpu().numpy()
-        if is_action_noise:
-            np.random.set_state(state)
-            np.random.randn(n, 3)
-        x_ic = self._initial_state(env)
-        theta_trim = np.rad2deg(x_ic[7])
-        from ..envs.phlabenv import _RefSignal
-        sw = refsig.widths(env.t_max)[1]
-        refs = [_RefSignal(levels[0], starts[0], theta_trim, sw, env.t_max), _RefSignal(levels[1], starts[1], 0.0, sw), lambda t: 0.0]
-        return self._episode_from_trace(agent, tr, n, x_ic, store_transition, refs)
+        f = self._fly(agent, 1, is_action_noise=is_action_noise, store_transition=store_transition, trace=True)
+        return self._collect(agent, f, store_transition=store_transition, want_history=True)[0]
 
     _ic_cache: Dict[int, np.ndarray] = {}
 
@@ -168,54 +212,83 @@ class Agent:
                     TD_loss.append(TD)
         return {'PG_obj': np.mean(pgs_obj) if pgs_obj else float('nan'), 'TD_loss': np.median(TD_loss) if TD_loss else float('nan')}
 
+    @staticmethod
+    def _validation_stats(eps):
+        scores = [np.sum(e.reward_lst) if not isinstance(e.reward_lst, _ReturnOnly) else e.reward_lst.total for e in eps]
+        lengths = [e.length for e in eps]
+        sms = [e.smoothness for e in eps]
+        return (np.mean(scores), np.std(scores), np.mean(lengths), np.std(lengths), eps[-1], np.median(sms), np.std(sms))
+
     def validate_agent(self, agent):
-        test_scores, episode_lengths, smoothness_lst = [], [], []
-        for _ in range(self.validation_tests):
-            last_episode = self.evaluate(agent, is_action_noise=False, store_transition=False)
-            test_scores.append(np.sum(last_episode.reward_lst))
-            episode_lengths.append(last_episode.length)
-            smoothness_lst.append(last_episode.smoothness)
-        return (np.mean(test_scores), np.std(test_scores), np.mean(episode_lengths), np.std(episode_lengths), last_episode,
-                np.median(smoothness_lst), np.std(smoothness_lst))
+        """agent.py:188-209: `validation_tests` episodes, none stored — flown as ONE launch of 5 trajectories."""
+        f = self._fly(agent, self.validation_tests, trace=bool(self.args.should_log))
+        return self._validation_stats(self._collect(agent, f, want_history=bool(self.args.should_log)))
 
     # ------------------------------------------------------------------------------------------------ generation
-    def evaluate_population(self):
-        """agent.py:229-245 as one fused launch. Returns (pop_fitness f64[pop] numpy, lengths list, device fitness)."""
+    def evaluate_population(self, sm_limit=0):
+        """agent.py:229-258 as one fused launch: every actor x (num_envs population references + validation_tests validation
+        references).  Returns (pop_fitness f64[pop] numpy, device fitness, per-actor record matrix numpy) — identical on
+        every rank."""
         n_envs = int(getattr(self.args, 'num_envs', self.args.num_evals))
-        self._count_before, self._gen_before = (self.num_frames, self.num_episodes), self.gen_frames
-        draws = [self.env.draw_reference() for _ in range(n_envs)]
+        n_val = self.validation_tests
+        E = n_envs + n_val
+        draws = [self.env.draw_reference() for _ in range(E)]
+        self._pop_draws = draws
         lv = torch.as_tensor(np.stack([d[0] for d in draws]), device=self.device)
         st = torch.as_tensor(np.stack([d[1] for d in draws]), device=self.device)
-        md = torch.full((n_envs,), self.env.mode_code, dtype=torch.int32, device=self.device)
-        want_sm = bool(getattr(self.args, 'population_smoothness', True))
-        fitness, r, (lo, hi) = engine.evaluate_population(self.pop.genomes, self.shape, lv, st, md, actions=want_sm,
-                                                          smooth_fitness=bool(self.args.smooth_fitness))
-        steps = r.steps.cpu().numpy() if r is not None else np.zeros((0, n_envs), dtype=np.int32)
-        self._last_smoothness = r.smoothness.cpu().numpy() if (r is not None and getattr(r, 'smoothness', None) is not None) else None
-        lengths = [self._final_time(int(s)) for s in steps.reshape(-1)[:256]]     # statistic only; bounded host work
-        if self.store_population_transitions and hi > lo:
-            # transitions of the last evaluation of every actor (agent.py:236-238), from a traced re-flight of that env
-            tr = rollout.population_rollout(self.pop.genomes[lo:hi], self.shape, lv[-1:].contiguous(), st[-1:].contiguous(), md[-1:], trace=True)
-            x_ic = self._initial_state(self.env)
-            tsteps = tr.steps[:, 0].cpu().numpy()
-            for a in range(hi - lo):
-                n = int(tsteps[a])
-                self._episode_from_trace(self.pop[lo + a], tr.trace[a, 0, :n].cpu().numpy(), n, x_ic, True, None)
-        else:
-            self.num_frames += int(steps[:, -1].sum()) if steps.size else 0
-            self.gen_frames += int(steps[:, -1].sum()) if steps.size else 0
-            self.num_episodes += hi - lo
-        world, _ = engine.world_info()
-        if world > 1:
-            # frame / episode counters drive the training loop (base/train.py:102); keep them identical on every rank
-            import torch.distributed as dist
-            f0, e0 = self._count_before
-            cnt = torch.tensor([self.num_frames - f0, self.num_episodes - e0, self.gen_frames - self._gen_before],
-                               dtype=torch.int64, device=self.device)
-            dist.all_reduce(cnt)
-            self.num_frames, self.num_episodes = f0 + int(cnt[0]), e0 + int(cnt[1])
-            self.gen_frames = self._gen_before + int(cnt[2])
-        return fitness.cpu().numpy(), lengths, fitness
+        md = torch.full((E,), self.env.mode_code, dtype=torch.int32, device=self.device)
+        want_sm = bool(getattr(self.args, 'population_smoothness', False)) or bool(self.args.smooth_fitness)
+        store = self.store_population_transitions
+        world, rank = engine.world_info()
+        pop = len(self.pop)
+        lo, hi = engine.shard_bounds(pop, world, rank)
+        horizon = self._horizon()
+        K = 4 + 3 * n_val + 4
+        rec = torch.zeros((hi - lo, K), dtype=torch.float64, device=self.device)
+        r = None
+        if hi > lo:
+            r = rollout.population_rollout(self.pop.genomes[lo:hi], self.shape, lv, st, md, horizon=horizon, actions=want_sm,
+                                           replay_env=(n_envs - 1) if store else None, sm_limit=sm_limit, fitness=False,
+                                           **self._eval_kw())
+            sm_all = None
+            if want_sm:
+                sm_all = rollout.smoothness(r.actions, r.steps)
+                r.actions = None
+            ret_p = r.returns[:, :n_envs]
+            if self.args.smooth_fitness:
+                ret_p = ret_p + sm_all[:, :n_envs]
+            stp = r.steps.to(torch.float64)
+            rec[:, 0] = ret_p.mean(dim=1)                                     # fitness (agent.py:245)
+            rec[:, 1] = stp[:, :n_envs].sum(1)                                # episode-length statistics
+            rec[:, 2] = (stp[:, :n_envs] ** 2).sum(1)
+            rec[:, 3] = stp[:, n_envs - 1]                                    # frames of the stored evaluation
+            rec[:, 4:4 + n_val] = r.returns[:, n_envs:]                       # validation episodes of every actor
+            rec[:, 4 + n_val:4 + 2 * n_val] = stp[:, n_envs:]
+            if sm_all is not None:
+                rec[:, 4 + 2 * n_val:4 + 3 * n_val] = sm_all[:, n_envs:]
+                rec[:, 4 + 3 * n_val] = sm_all[:, :n_envs].sum(1)
+                rec[:, 5 + 3 * n_val] = (sm_all[:, :n_envs] ** 2).sum(1)
+                rec[:, 6 + 3 * n_val] = 1.0
+        rec_all = engine.gather_rows(rec, pop, world, rank)
+        self._last_result = r
+        if store:
+            # the stored transitions of EVERY actor reach EVERY rank (identical shared / per-actor buffers on all ranks)
+            rows = r.replay if r is not None else torch.zeros((0, horizon, rollout.REPLAY_COLS), dtype=torch.float32, device=self.device)
+            rows_all = engine.gather_rows(rows.reshape(rows.shape[0], -1), pop, world, rank).reshape(pop, horizon, rollout.REPLAY_COLS)
+            steps_all = rec_all[:, 3].to(torch.int64)
+            sel = torch.arange(horizon, device=self.device)[None, :] < steps_all[:, None]
+            self.replay_buffer.add_rows(rows_all[sel])
+            actors = torch.arange(pop, device=self.device)
+            self.pop.buffers.append(actors, rows_all, sel)
+            self.pop.critical_buffers.append(actors, rows_all, sel & (rows_all[..., 19] > 0.5))
+        rec_host = rec_all.cpu().numpy()
+        if r is not None:
+            r.check()
+        frames = int(rec_host[:, 3].sum())
+        self.num_frames += frames
+        self.gen_frames += frames
+        self.num_episodes += pop
+        return rec_host[:, 0].copy(), rec_all[:, 0].contiguous(), rec_host
 
     def train(self):
         self.iterations += 1
@@ -224,32 +297,51 @@ class Agent:
         test_sd = sm_sd = elite_index = pop_novelty = -1.
         ep_len_avg = ep_len_sd = 0.
         pop_fitness = None
+        args = self.args
+        # RL exploration episode (agent.py:267-268): independent of the population -> side stream, launched first.  The RL
+        # validation (:273-275) reads the RL actor AFTER train_rl; when no gradient step can happen it joins the side stream.
+        early_validation = args.frac_frames_train == 0
+        f_explore = self._fly(self.rl_agent, 1, is_action_noise=True, store_transition=True, trace=bool(args.should_log), stream=self._side)
+        f_rlval = self._fly(self.rl_agent, self.validation_tests, trace=bool(args.should_log), stream=self._side) if early_validation else None
         if len(self.pop):
-            pop_fitness, lengths, dev_fitness = self.evaluate_population()
-            if self._last_smoothness is not None:      # K6: per-episode action smoothness on the device (agent.py:242-243)
-                sm, sm_sd = float(np.mean(self._last_smoothness)), float(np.std(self._last_smoothness))
+            n_val = self.validation_tests
+            pop_fitness, dev_fitness, rec = self.evaluate_population(sm_limit=-2)
+            n_envs = int(getattr(args, 'num_envs', args.num_evals))
+            n_ep = len(self.pop) * n_envs
+            dt = self.env.dt
+            mean_steps = rec[:, 1].sum() / n_ep
+            ep_len_avg = mean_steps * dt
+            ep_len_sd = float(np.sqrt(max(rec[:, 2].sum() / n_ep - mean_steps ** 2, 0.0))) * dt
+            if rec[:, 6 + 3 * n_val].any():      # K6: per-episode action smoothness on the device (agent.py:242-243)
+                sm = rec[:, 4 + 3 * n_val].sum() / n_ep
+                sm_sd = float(np.sqrt(max(rec[:, 5 + 3 * n_val].sum() / n_ep - sm ** 2, 0.0)))
             else:
                 sm, sm_sd = float('nan'), float('nan')
-            ep_len_avg, ep_len_sd = np.mean(lengths), np.std(lengths)
             best_train_fitness = np.max(pop_fitness)
             worst_train_fitness = np.min(pop_fitness)
             population_avg = np.average(pop_fitness)
-            self.champion = self.pop[int(np.argmax(pop_fitness))]
+            ci = int(np.argmax(pop_fitness))
+            self.champion = self.pop[ci]
             self.champion_actor = self.champion.actor
-            test_score, test_sd, _, _, last_episode, _, _ = self.validate_agent(self.champion)
-            if self.args.should_log:
-                self.champion_history = last_episode.get_history()
+            # validate_agent(champion) (:255-258): the champion's row of the validation columns flown with the population
+            test_score, test_sd = float(np.mean(rec[ci, 4:4 + n_val])), float(np.std(rec[ci, 4:4 + n_val]))
+            if args.should_log:
+                last = self.validate_agent_on(self.champion, self._pop_draws[-1])
+                self.champion_history = last.get_history()
             elite_index = self.evolver.epoch(self.pop, dev_fitness)
         # RL half (agent.py:267-281)
-        self.evaluate(self.rl_agent, is_action_noise=True, store_transition=True)
+        self._collect(self.rl_agent, f_explore, store_transition=True)
         rl_train_scores = self.train_rl(self.gen_frames)
-        rl_reward, rl_std, rl_ep_len, rl_ep_std, rl_episode, rl_sm, rl_sm_sd = self.validate_agent(self.rl_agent)
-        if self.args.pop_size == 0:
+        if f_rlval is None:
+            f_rlval = self._fly(self.rl_agent, self.validation_tests, trace=bool(args.should_log))
+        rl_reward, rl_std, rl_ep_len, rl_ep_std, rl_episode, rl_sm, rl_sm_sd = self._validation_stats(
+            self._collect(self.rl_agent, f_rlval, want_history=bool(args.should_log)))
+        if args.pop_size == 0:
             ep_len_avg, ep_len_sd = rl_ep_len, rl_ep_std
-        if self.args.should_log:
+        if args.should_log:
             self.rl_history = rl_episode.get_history()
         # actor injection (agent.py:283-294)
-        if self.args.pop_size and self.iterations % self.args.rl_to_ea_synch_period == 0:
+        if args.pop_size and self.iterations % args.rl_to_ea_synch_period == 0:
             replace_index = int(np.argmin(pop_fitness))
             if replace_index == elite_index:
                 replace_index = (replace_index + 1) % len(self.pop)
@@ -262,6 +354,21 @@ class Agent:
             'rl_smoothness_std': rl_sm_sd, 'rl_std': rl_std, 'avg_ep_len': ep_len_avg, 'ep_len_sd': ep_len_sd,
             'PG_obj': rl_train_scores['PG_obj'], 'TD_loss': rl_train_scores['TD_loss'], 'pop_novelty': pop_novelty,
         }
+
+    def validate_agent_on(self, agent, draw) -> Episode:
+        """one traced episode on a GIVEN reference (the champion's last validation episode, for its logged history)."""
+        env = self.env
+        lv = torch.as_tensor(draw[0][None], device=self.device)
+        st = torch.as_tensor(draw[1][None], device=self.device)
+        md = torch.tensor([env.mode_code], dtype=torch.int32, device=self.device)
+        f = _Flight()
+        f.levels, f.starts, f.n, f.noise_state, f.stream = [draw[0]], [draw[1]], 1, None, None
+        f.r = rollout.population_rollout(self._genome_of(agent), self.shape, lv, st, md, trace=True, horizon=self._horizon(),
+                                         actions=True, **self._eval_kw())
+        f.r.smoothness = rollout.smoothness(f.r.actions, f.r.steps)
+        f.event = torch.cuda.Event()
+        f.event.record()
+        return self._collect(agent, f, want_history=True)[0]
 
     def save_agent(self, parameters, elite_index: int = None) -> None:
         """agent.py:317-352: evo_nets.pkl ({'actor_i': state_dict}), elite_net.pkl, rl_net.pkl, state histories."""
@@ -278,3 +385,21 @@ class Agent:
         if self.rl_history is not None:
             np.savetxt(os.path.join(parameters.save_foldername, 'rl_statehistory_episode%d.txt' % self.num_episodes),
                        self.rl_history, header=str(self.num_episodes))
+
+
+class _ReturnOnly:
+    """reward list of an episode whose per-step record was not requested: only the sum is known."""
+
+    def __init__(self, total):
+        self.total = total
+
+    def __len__(self):
+        return 0
+
+
+class _null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False

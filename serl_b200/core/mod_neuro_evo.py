@@ -63,6 +63,11 @@ class SSNE:
 def _copy_buffers(master, replacee):
     if master is replacee:
         return
+    owner = getattr(master.buffer, 'owner', None)
+    if owner is not None and owner is getattr(replacee.buffer, 'owner', None):      # device-resident per-actor rings
+        owner.copy_actor(master.buffer.index, replacee.buffer.index)
+        master.critical_buffer.owner.copy_actor(master.critical_buffer.index, replacee.critical_buffer.index)
+        return
     replacee.buffer.reset()
     replacee.buffer.add_content_of(master.buffer)
     replacee.critical_buffer.reset()

@@ -42,8 +42,9 @@ class Critic(nn.Module):
 class TD3:
     def __init__(self, args):
         self.args = args
-        self.buffer = replay_memory.ReplayMemory(args.individual_bs, args.device)
-        self.critical_buffer = replay_memory.ReplayMemory(args.individual_bs, args.device)
+        mem = replay_memory.DeviceReplayMemory if torch.device(args.device).type == 'cuda' else replay_memory.ReplayMemory
+        self.buffer = mem(args.individual_bs, args.device)
+        self.critical_buffer = mem(args.individual_bs, args.device)
         self.actor = Actor(args, init=True).to(args.device)
         self.actor_target = Actor(args, init=True).to(args.device)
         self.actor_optim = Adam(self.actor.parameters(), lr=args.lr)

@@ -281,6 +281,7 @@ struct RolloutArgs {
     const int* env_order;           // optional [n_envs]: lane slot -> env index
     float* replay; int replay_env;  // optional [pop, horizon, SERL_REPLAY_COLS] transitions of one env per actor
     int* status;                    // optional device status word
+    int sm_limit;                   // > 0: CTAs of the persistent kernel (SMs) this launch may use
     // persistent schedule
     const float* wt;                // [pop][P4] genomes in the shared-memory layout (transposed matrices), 16-byte aligned rows
     int P4;                         // row stride of wt / smem slot size in floats (multiple of 4)
@@ -366,6 +367,8 @@ __device__ void env_step(Env& e, const RolloutArgs& ar, size_t traj, int actor, 
             U[i] = -bound + (double)t2 * (bound - (-bound));
         }
     }
+    // a NaN action would be squashed to a bound by the plant's input saturation (as in the reference binary): report it
+    if (ar.status && !isfinite(act_d[0] + act_d[1] + act_d[2])) atomicOr(ar.status, SERL_STATUS_NONFINITE);
     apply_fault(e.fault, U, cmd);
     double xo[12];
 #pragma unroll
@@ -851,7 +854,7 @@ rollout_kernel_persist(RolloutArgs ar)
         } else if (valid) {
             ar.returns[traj] = e.ret;
             ar.steps[traj] = e.k;
-            if (ar.status && !isfinite(e.ret)) atomicOr(ar.status, SERL_STATUS_NONFINITE);
+            if (ar.status && !isfinite(e.ret + e.X[3] + e.X[7] + e.X[9])) atomicOr(ar.status, SERL_STATUS_NONFINITE);   // NaN actions poison the state at once
         }
     }
 }
@@ -885,7 +888,7 @@ rollout_kernel_simple(RolloutArgs ar)
     }
     ar.returns[traj] = e.ret;
     ar.steps[traj] = e.k;
-    if (ar.status && !isfinite(e.ret)) atomicOr(ar.status, SERL_STATUS_NONFINITE);
+    if (ar.status && !isfinite(e.ret + e.X[3] + e.X[7] + e.X[9])) atomicOr(ar.status, SERL_STATUS_NONFINITE);   // NaN actions poison the state at once
 }
 
 // ---- Actor.forward for a batch of observations (same device functions as the rollout) --------------------------
@@ -1117,7 +1120,7 @@ template <int H, bool TABS>
 static cudaError_t launch_persist(RolloutArgs& ar, int apc_max, cudaStream_t s, void** scratch)
 {
     constexpr int TABN2 = (PT_TOTAL + SERL_PLANT_COUNT * PLANT_NPV + 1) & ~1;
-    const int sms = device_sms();
+    const int sms = ar.sm_limit > 0 && ar.sm_limit < device_sms() ? ar.sm_limit : device_sms();
     int apc, wps;
     choose_shape(ar.pop, ar.n_envs, apc_max, sms, &apc, &wps);
     static int f_apc = -1, f_wps = -1;       // experiment knobs
@@ -1189,7 +1192,7 @@ static int rollout_impl(const serl_rollout_desc& d, void* stream)
     ar.pop = d.pop;
     ar.t_max = d.t_max > 0.0 ? d.t_max : 20.0;
     ar.smooth_w = d.t_max > 0.0 ? d.smooth_width : 3.0;
-    ar.env_order = d.d_env_order; ar.replay = d.d_replay; ar.replay_env = d.replay_env; ar.status = d.d_status;
+    ar.env_order = d.d_env_order; ar.replay = d.d_replay; ar.replay_env = d.replay_env; ar.status = d.d_status; ar.sm_limit = d.sm_limit;
     ar.P4 = (ar.P + 3) & ~3;
     const int H = shape->hidden;
     cudaError_t e;

@@ -25,21 +25,28 @@ def shard_bounds(pop, world, rank):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def gather_fitness(local, pop, world, rank, group=None):
-    """all-gather of unequal contiguous blocks -> fitness[pop] on every rank (same dtype/device as `local`)."""
+def gather_rows(local, pop, world, rank, group=None):
+    """all-gather of unequal contiguous actor blocks: local [n_local, ...] -> [pop, ...] on every rank."""
     if world == 1:
         return local
     blk = (pop + world - 1) // world
-    pad = torch.zeros(blk, dtype=local.dtype, device=local.device)
-    pad[:local.numel()] = local
-    out = torch.empty(world * blk, dtype=local.dtype, device=local.device)
-    dist.all_gather_into_tensor(out, pad, group=group) if out.is_cuda else \
-        dist.all_gather(list(out.view(world, blk).unbind(0)), pad, group=group)
+    pad = torch.zeros((blk,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[:local.shape[0]] = local
+    out = torch.empty((world * blk,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    if out.is_cuda:
+        dist.all_gather_into_tensor(out, pad, group=group)
+    else:
+        dist.all_gather(list(out.view((world, blk) + tuple(local.shape[1:])).unbind(0)), pad, group=group)
     parts = []
     for r in range(world):
         lo, hi = shard_bounds(pop, world, r)
         parts.append(out[r * blk:r * blk + (hi - lo)])
     return torch.cat(parts)
+
+
+def gather_fitness(local, pop, world, rank, group=None):
+    """fitness[pop] on every rank (same dtype/device as `local`): the one collective of the path."""
+    return gather_rows(local, pop, world, rank, group)
 
 
 def evaluate_population(genomes, shape, ref_levels, ref_starts, env_mode, horizon=rollout.HORIZON, group=None,

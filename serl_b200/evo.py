@@ -232,6 +232,7 @@ def epoch_flat(weights, fitness, shape, elite_fraction=0.2, mutation_prob=0.9, m
     fitness = fitness.to(device=weights.device, dtype=torch.float64).contiguous()
     import time
     num_elitists = max(int(elite_fraction * pop), 1)
+    torch.cuda.current_stream(weights.device).synchronize()     # the fitness may still be in flight: keep its wait out of select_ms
     t0 = time.perf_counter()
     index_rank, offs_raw = select_device(fitness, num_elitists)
     t1 = time.perf_counter()

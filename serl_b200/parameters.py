@@ -60,8 +60,12 @@ class Parameters:
             self.mutation_mag = 0.0247682869654
             self.mutation_batch_size = self.batch_size
             self.mut_type = g('mut_type', 'normal')
-            if self.mut_type == 'proximal' and not hasattr(cla, '_explicit_mut_type'):
-                self.mut_type = 'normal'          # base/train.py's CLI default; see module docstring
+            if self.mut_type in ('proximal', 'safe'):
+                import warnings
+                warnings.warn("mut_type '%s' (base/train.py's CLI default is 'proximal') is not implemented by the B200 engine; "
+                              "running the classic Gaussian mutation (mut_type 'normal', mod_neuro_evo.py:329-369) instead"
+                              % self.mut_type, RuntimeWarning, stacklevel=2)
+                self.mut_type = 'normal'
             self.distil_crossover = False
             self.distil_type = g('distil_type', 'distance')
             self.crossover_prob = 0.0

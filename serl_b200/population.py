@@ -6,7 +6,7 @@ torch.manual_seed, base/train.py:89, agent.py:23-24), so the initial genomes are
 """
 import torch
 
-from .core import genetic_agent
+from .core import genetic_agent, replay_memory
 from . import rollout
 
 
@@ -24,6 +24,12 @@ class PopulationList(list):
             self.genomes[i].copy_(a.actor.flat())
             a.actor.bind(self.genomes[i])
             a.index = i
+        # GeneticAgent.buffer / .critical_buffer of every actor: two device tensors, allocated on first use
+        self.buffers = replay_memory.PopulationBuffers(args.pop_size, args.individual_bs, self.device)
+        self.critical_buffers = replay_memory.PopulationBuffers(args.pop_size, args.individual_bs, self.device)
+        for i, a in enumerate(agents):
+            a.buffer = replay_memory.ActorBuffer(self.buffers, i)
+            a.critical_buffer = replay_memory.ActorBuffer(self.critical_buffers, i)
         self.extend(agents)
 
     def isEmpty(self):            # the reference calls this on its (list) population (agent.py:326)

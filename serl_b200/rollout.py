@@ -64,10 +64,12 @@ def variant_sorted_order(env_mode):
 
 
 def population_rollout(weights, shape, ref_levels, ref_starts, env_mode, horizon=HORIZON, trace=False, out=None, action_noise=None,
-                       actions=False, t_max=None, smooth_width=None, env_order=None, replay_env=None, status=True):
+                       actions=False, t_max=None, smooth_width=None, env_order=None, replay_env=None, status=True, sm_limit=0,
+                       fitness=True):
     """weights [pop,P] fp32 cuda; ref_levels/ref_starts [n_envs,2,6] f64 cuda; env_mode [n_envs] int32 cuda.
     env_order: optional int32 [n_envs] permutation (see variant_sorted_order); replay_env: record the transitions of that env
-    of every actor into result.replay [pop, horizon, REPLAY_COLS]; status: carry the device status word (result.check())."""
+    of every actor into result.replay [pop, horizon, REPLAY_COLS]; status: carry the device status word (result.check());
+    sm_limit: SMs this launch may occupy (0 = all); fitness=False skips the per-actor mean kernel."""
     if not weights.is_cuda:
         raise _native.NativeError('population_rollout needs CUDA tensors (no CPU fallback)')
     L = _native.lib()
@@ -87,7 +89,7 @@ def population_rollout(weights, shape, ref_levels, ref_starts, env_mode, horizon
     if out is None:
         r.returns = torch.empty((pop, n_envs), dtype=torch.float64, device=dev)
         r.steps = torch.empty((pop, n_envs), dtype=torch.int32, device=dev)
-        r.fitness = torch.empty((pop,), dtype=torch.float64, device=dev)
+        r.fitness = torch.empty((pop,), dtype=torch.float64, device=dev) if fitness else None
         r.trace = None
         r.smoothness = None
         r.actions = torch.empty((pop, n_envs, horizon, 3), dtype=torch.float32, device=dev) if actions else None
@@ -110,6 +112,9 @@ def population_rollout(weights, shape, ref_levels, ref_starts, env_mode, horizon
     d.d_env_order = p(env_order)
     d.d_replay, d.replay_env = p(getattr(r, 'replay', None)), int(replay_env if replay_env is not None else 0)
     d.d_status = p(getattr(r, 'status', None))
+    if sm_limit < 0:         # leave -sm_limit SMs to concurrent small launches
+        sm_limit = max(1, torch.cuda.get_device_properties(dev).multi_processor_count + int(sm_limit))
+    d.sm_limit = int(sm_limit)
     _native.check(L.serl_rollout_run(ctypes.byref(d), stream), 'serl_rollout_run')
     return r
 

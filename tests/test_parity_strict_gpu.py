@@ -191,17 +191,19 @@ def test_replay_export_equals_trace_rebuilt_transitions():
     rp = r.replay.cpu().numpy()
     tr = r.trace.cpu().numpy()
     stp = r.steps.cpu().numpy()
+    from oracle import plant as OP
+    x_ic = np.asarray(OP.make_plant('h2000_v90', 'port').initial_state())     # reset(): obs = [0, 0, 0, IC[p, q, r, alpha]]
     for a in range(4):
         n = stp[a, 2]
         t = tr[a, 2, :n]
         next_obs = np.hstack((t[:, 19:22], t[:, [0, 1, 2, 4]])).astype(np.float32)
-        obs = np.vstack((np.hstack((np.zeros(3), t[0, [0, 1, 2, 4]]))[None].astype(np.float32), next_obs[:-1]))
+        obs = np.vstack((np.hstack((np.zeros(3), x_ic[[0, 1, 2, 4]]))[None].astype(np.float32), next_obs[:-1]))
         assert np.array_equal(rp[a, :n, 0:7], obs)
         assert np.array_equal(rp[a, :n, 7:10], t[:, 16:19].astype(np.float32))
         assert np.array_equal(rp[a, :n, 10:17], next_obs)
         assert np.array_equal(rp[a, :n, 17], t[:, 15].astype(np.float32))
         done = np.zeros(n, dtype=np.float32)
-        done[-1] = 1.0 if (n < 2001 or True) else 0.0
+        done[-1] = 1.0
         assert np.array_equal(rp[a, :n, 18], done)
         cost = (np.rad2deg(np.abs(t[:, 4])) > 11.0) | (np.rad2deg(np.abs(t[:, 6])) > 0.75 * np.deg2rad(75.0)) | (t[:, 3] < 90.0 / 3)
         assert np.array_equal(rp[a, :n, 19], cost.astype(np.float32))
