@@ -192,7 +192,7 @@ def timed_region(step_fn, steps, warmup, flush, sync_all):
     return t_begin.elapsed_time(t_end), float(np.mean([a.elapsed_time(b) for a, b in ev])), res
 
 
-def agent_train_timing(dev, pop, n_envs, generations=3):
+def agent_train_timing(dev, pop, n_envs, generations=4):
     """One generation through the public API (Agent.train, base/core/agent.py:211-315 mirror) at the bench configuration,
     EA loop only (-test_ea: no TD3 gradient steps; the RL exploration + validation episodes still fly), wall clock."""
     import random
@@ -217,13 +217,13 @@ def agent_train_timing(dev, pop, n_envs, generations=3):
     ag.pop.genomes.copy_(torch.from_numpy(population(pop)).to(dev))
     times, stats = [], None
     for g in range(generations + 1):
-        ag.pop.genomes.copy_(torch.from_numpy(population(pop)).to(dev))       # keep flying full episodes: a trained population
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         stats = ag.train()
         torch.cuda.synchronize()
         if g > 0:
             times.append(1e3 * (time.perf_counter() - t0))
+    ag.last_timing = dict(ag.timing)
     return float(np.mean(times)), stats, ag
 
 
@@ -412,9 +412,12 @@ def run_ours(args):
         if not args.no_agent:
             ag_ms, ag_stats, ag = agent_train_timing(dev, POP, N_ENVS)
             agent_line = {'generation_ms': ag_ms, 'population_rollout_ms': m['kern_ms'], 'ratio_to_population_rollout': ag_ms / m['kern_ms'],
-                          'what': 'wall clock of Agent.train() (EA loop, -test_ea): RL exploration + RL validation episodes on a side '
-                                  'stream, population x (128 + 5 validation) envs in one launch, SSNE.epoch (K2-K5 + host planner), stats',
-                          'frames_per_generation': int(ag.gen_frames), 'test_score': float(ag_stats['test_score'])}
+                          'what': 'wall clock of Agent.train() (EA loop, -test_ea): RL exploration + RL validation episodes on a side stream during the '
+                                  'population rollout, champion validation (5 x 2001-step trajectories, ~0.15 s of serial latency) on the side '
+                                  'stream during SSNE.epoch (K2-K5 + host planner), stats',
+                          'frames_per_generation': int(ag.gen_frames), 'test_score': float(ag_stats['test_score']),
+                          'phases_ms_last_generation': ag.last_timing,
+                          'speculative_champion_validation': {'hits': int(ag.spec_hits), 'tries': int(ag.spec_tries)}}
             del ag
 
     if rank == 0:

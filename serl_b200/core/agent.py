@@ -1,11 +1,13 @@
 """Mirror of base/core/agent.py (Agent :13-352): same constructor, evaluate(), train(), validate_agent(), save_agent() and
 stats keys, with the per-generation fitness hot path on the GPU:
 
-  * the population loop `for net in pop: for i in range(num_evals): evaluate(net)` (:234-241) AND the champion's
-    validation episodes (:255-258) are ONE fused rollout launch over pop x (num_envs + 5) trajectories
-    (serl_b200/rollout.py, csrc/rollout.cu), sharded over ranks when torch.distributed is initialised
-    (serl_b200/engine.py): every actor also flies the 5 validation references (+4 % work), the champion's row is read
-    once the ranking is known — no serial 150 ms single-trajectory launch after the rollout;
+  * the population loop `for net in pop: for i in range(num_evals): evaluate(net)` (:234-241) is ONE fused rollout launch
+    over pop x num_envs trajectories (serl_b200/rollout.py, csrc/rollout.cu), sharded over ranks when torch.distributed
+    is initialised (serl_b200/engine.py);
+  * validate_agent (:188-209) flies its 5 episodes as ONE launch; the champion's validation (:255-258) runs on a side
+    stream while SSNE.epoch works on the main stream (a single 2001-step trajectory is ~0.15 s of serial latency however
+    few of them there are — the one part of a generation that cannot be hidden, since the champion is only known once the
+    population has been ranked);
   * the transitions of the stored evaluation (:101-112, `store_transition=(i == num_evals-1)`) are written by the kernel
     (K1 replay rows) and appended on the device to the shared replay buffer and the per-actor buffers — no traced
     re-flight, no per-actor host loop;
@@ -34,7 +36,7 @@ from ..population import PopulationList
 
 class _Flight:
     """an asynchronous launch of n episodes of ONE actor (result tensors stay on the device until collected)."""
-    __slots__ = ('r', 'levels', 'starts', 'n', 'noise_state', 'stream', 'event')
+    __slots__ = ('r', 'levels', 'starts', 'n', 'noise_state', 'stream', 'event', 'keep')
 
 
 class Agent:
@@ -64,6 +66,9 @@ class Agent:
         self.champion_history = None
         self.store_population_transitions = args.frac_frames_train > 0 or getattr(args, 'mut_type', 'normal') in ('proximal', 'safe')
         self._side = torch.cuda.Stream(self.device, priority=-1)
+        self.speculative_validations = int(getattr(args, 'speculative_validations', 3))
+        self._spec_streams = [torch.cuda.Stream(self.device, priority=-1) for _ in range(self.speculative_validations)]
+        self.spec_hits = self.spec_tries = 0
         self.timing = {}
 
     # ------------------------------------------------------------------------------------------------ episodes
@@ -86,10 +91,10 @@ class Agent:
         env = self.env
         return {} if env.t_max == 20 else {'t_max': float(env.t_max), 'smooth_width': refsig.widths(env.t_max)[1]}
 
-    def _fly(self, agent, n, is_action_noise=False, store_transition=False, trace=False, stream=None) -> _Flight:
-        """launch n episodes of one actor (fresh reference signals each) without waiting for them."""
+    def _fly(self, agent, n, is_action_noise=False, store_transition=False, trace=False, stream=None, copy_genome=False, draws=None) -> _Flight:
+        """launch n episodes of one actor (fresh reference signals each, or the given `draws`) without waiting for them."""
         env = self.env
-        draws = [env.draw_reference() for _ in range(n)]
+        draws = draws if draws is not None else [env.draw_reference() for _ in range(n)]
         f = _Flight()
         f.levels, f.starts, f.n = [d[0] for d in draws], [d[1] for d in draws], n
         f.noise_state = None
@@ -102,21 +107,26 @@ class Agent:
             f.noise_state = np.random.get_state()
             z = np.random.randn(horizon, 3)
             noise_host = np.clip(self.args.noise_sd * z, -self.args.noise_clip, self.args.noise_clip).astype(np.float32).reshape(1, 1, -1, 3)
-        genome = self._genome_of(agent)
         f.stream = stream
         ctx = torch.cuda.stream(stream) if stream is not None else _null()
+        pre = self._genome_of(agent).clone() if copy_genome else None        # copied on the main stream, before later edits
         if stream is not None:
             stream.wait_stream(torch.cuda.current_stream(self.device))        # genomes / weights written on the main stream
         with ctx:
-            lv = torch.as_tensor(np.stack(f.levels), device=self.device)
-            st = torch.as_tensor(np.stack(f.starts), device=self.device)
+            genome = pre if pre is not None else self._genome_of(agent)
+            if stream is not None:
+                genome.record_stream(stream)
+            # pinned staging + non_blocking: a pageable host->device copy would wait for the kernels queued on this stream
+            lv = _to_device(np.stack(f.levels), self.device)
+            st = _to_device(np.stack(f.starts), self.device)
             md = torch.full((n,), env.mode_code, dtype=torch.int32, device=self.device)
-            noise = torch.as_tensor(noise_host, device=self.device) if noise_host is not None else None
+            noise = _to_device(noise_host, self.device) if noise_host is not None else None
             f.r = rollout.population_rollout(genome, self.shape, lv, st, md, trace=trace, action_noise=noise, horizon=horizon,
                                              actions=True, replay_env=0 if store_transition else None, **self._eval_kw())
             f.r.smoothness = rollout.smoothness(f.r.actions, f.r.steps)
             f.event = torch.cuda.Event()
             f.event.record()
+            f.keep = (genome, lv, st, md, noise)      # inputs stay alive until the flight is collected
         return f
 
     def _store_rows(self, agent, rows, n):
@@ -226,25 +236,21 @@ class Agent:
 
     # ------------------------------------------------------------------------------------------------ generation
     def evaluate_population(self, sm_limit=0):
-        """agent.py:229-258 as one fused launch: every actor x (num_envs population references + validation_tests validation
-        references).  Returns (pop_fitness f64[pop] numpy, device fitness, per-actor record matrix numpy) — identical on
-        every rank."""
+        """agent.py:229-245 as one fused launch: every actor x num_envs references.  Returns (pop_fitness f64[pop] numpy,
+        device fitness, per-actor record matrix numpy [fitness, sum len, sum len^2, stored frames, sum sm, sum sm^2, has sm])
+        — identical on every rank."""
         n_envs = int(getattr(self.args, 'num_envs', self.args.num_evals))
-        n_val = self.validation_tests
-        E = n_envs + n_val
-        draws = [self.env.draw_reference() for _ in range(E)]
-        self._pop_draws = draws
-        lv = torch.as_tensor(np.stack([d[0] for d in draws]), device=self.device)
-        st = torch.as_tensor(np.stack([d[1] for d in draws]), device=self.device)
-        md = torch.full((E,), self.env.mode_code, dtype=torch.int32, device=self.device)
+        draws = [self.env.draw_reference() for _ in range(n_envs)]
+        lv = _to_device(np.stack([d[0] for d in draws]), self.device)
+        st = _to_device(np.stack([d[1] for d in draws]), self.device)
+        md = torch.full((n_envs,), self.env.mode_code, dtype=torch.int32, device=self.device)
         want_sm = bool(getattr(self.args, 'population_smoothness', False)) or bool(self.args.smooth_fitness)
         store = self.store_population_transitions
         world, rank = engine.world_info()
         pop = len(self.pop)
         lo, hi = engine.shard_bounds(pop, world, rank)
         horizon = self._horizon()
-        K = 4 + 3 * n_val + 4
-        rec = torch.zeros((hi - lo, K), dtype=torch.float64, device=self.device)
+        rec = torch.zeros((hi - lo, 7), dtype=torch.float64, device=self.device)
         r = None
         if hi > lo:
             r = rollout.population_rollout(self.pop.genomes[lo:hi], self.shape, lv, st, md, horizon=horizon, actions=want_sm,
@@ -254,21 +260,16 @@ class Agent:
             if want_sm:
                 sm_all = rollout.smoothness(r.actions, r.steps)
                 r.actions = None
-            ret_p = r.returns[:, :n_envs]
-            if self.args.smooth_fitness:
-                ret_p = ret_p + sm_all[:, :n_envs]
+            ret_p = r.returns + sm_all if self.args.smooth_fitness else r.returns
             stp = r.steps.to(torch.float64)
             rec[:, 0] = ret_p.mean(dim=1)                                     # fitness (agent.py:245)
-            rec[:, 1] = stp[:, :n_envs].sum(1)                                # episode-length statistics
-            rec[:, 2] = (stp[:, :n_envs] ** 2).sum(1)
+            rec[:, 1] = stp.sum(1)                                            # episode-length statistics
+            rec[:, 2] = (stp ** 2).sum(1)
             rec[:, 3] = stp[:, n_envs - 1]                                    # frames of the stored evaluation
-            rec[:, 4:4 + n_val] = r.returns[:, n_envs:]                       # validation episodes of every actor
-            rec[:, 4 + n_val:4 + 2 * n_val] = stp[:, n_envs:]
             if sm_all is not None:
-                rec[:, 4 + 2 * n_val:4 + 3 * n_val] = sm_all[:, n_envs:]
-                rec[:, 4 + 3 * n_val] = sm_all[:, :n_envs].sum(1)
-                rec[:, 5 + 3 * n_val] = (sm_all[:, :n_envs] ** 2).sum(1)
-                rec[:, 6 + 3 * n_val] = 1.0
+                rec[:, 4] = sm_all.sum(1)
+                rec[:, 5] = (sm_all ** 2).sum(1)
+                rec[:, 6] = 1.0
         rec_all = engine.gather_rows(rec, pop, world, rank)
         self._last_result = r
         if store:
@@ -300,42 +301,74 @@ class Agent:
         args = self.args
         # RL exploration episode (agent.py:267-268): independent of the population -> side stream, launched first.  The RL
         # validation (:273-275) reads the RL actor AFTER train_rl; when no gradient step can happen it joins the side stream.
+        import time as _time
+        tm = self.timing = {}
+        t_prev = [_time.perf_counter()]
+
+        def lap(name):
+            now = _time.perf_counter()
+            tm[name] = tm.get(name, 0.0) + 1e3 * (now - t_prev[0])
+            t_prev[0] = now
         early_validation = args.frac_frames_train == 0
         f_explore = self._fly(self.rl_agent, 1, is_action_noise=True, store_transition=True, trace=bool(args.should_log), stream=self._side)
+        lap('launch_exploration')
         f_rlval = self._fly(self.rl_agent, self.validation_tests, trace=bool(args.should_log), stream=self._side) if early_validation else None
+        lap('launch_rl_flights')
+        f_champ = None
         if len(self.pop):
-            n_val = self.validation_tests
-            pop_fitness, dev_fitness, rec = self.evaluate_population(sm_limit=-2)
+            # Speculative champion validation: the champion is only known after the ranking, and its 5 validation episodes
+            # are ~0.15 s of serial latency.  The ranked elites of the previous generation survive unchanged (and so do
+            # their protected clones), and one of the best of them usually wins again: their validation episodes are
+            # launched NOW, next to the population rollout; a miss falls back to the serial launch.
+            val_draws = [self.env.draw_reference() for _ in range(self.validation_tests)]
+            spec = {}
+            plan = getattr(self.evolver, 'last_plan', None)
+            if plan is not None and self.speculative_validations > 0:
+                for j, (o, c) in enumerate(list(zip(plan.elitist_index, plan.new_elitists))[:self.speculative_validations]):
+                    spec[o] = spec[c] = self._fly(self.pop[o], self.validation_tests, trace=bool(args.should_log),
+                                                  stream=self._spec_streams[j], draws=val_draws)
+            lap('launch_speculative_validation')
+            pop_fitness, dev_fitness, rec = self.evaluate_population(sm_limit=-(2 + len(spec) // 2))
+            lap('evaluate_population')
             n_envs = int(getattr(args, 'num_envs', args.num_evals))
             n_ep = len(self.pop) * n_envs
             dt = self.env.dt
             mean_steps = rec[:, 1].sum() / n_ep
             ep_len_avg = mean_steps * dt
             ep_len_sd = float(np.sqrt(max(rec[:, 2].sum() / n_ep - mean_steps ** 2, 0.0))) * dt
-            if rec[:, 6 + 3 * n_val].any():      # K6: per-episode action smoothness on the device (agent.py:242-243)
-                sm = rec[:, 4 + 3 * n_val].sum() / n_ep
-                sm_sd = float(np.sqrt(max(rec[:, 5 + 3 * n_val].sum() / n_ep - sm ** 2, 0.0)))
+            if rec[:, 6].any():                  # K6: per-episode action smoothness on the device (agent.py:242-243)
+                sm = rec[:, 4].sum() / n_ep
+                sm_sd = float(np.sqrt(max(rec[:, 5].sum() / n_ep - sm ** 2, 0.0)))
             else:
                 sm, sm_sd = float('nan'), float('nan')
             best_train_fitness = np.max(pop_fitness)
             worst_train_fitness = np.min(pop_fitness)
             population_avg = np.average(pop_fitness)
-            ci = int(np.argmax(pop_fitness))
-            self.champion = self.pop[ci]
+            self.champion = self.pop[int(np.argmax(pop_fitness))]
             self.champion_actor = self.champion.actor
-            # validate_agent(champion) (:255-258): the champion's row of the validation columns flown with the population
-            test_score, test_sd = float(np.mean(rec[ci, 4:4 + n_val])), float(np.std(rec[ci, 4:4 + n_val]))
-            if args.should_log:
-                last = self.validate_agent_on(self.champion, self._pop_draws[-1])
-                self.champion_history = last.get_history()
+            # validate_agent(champion) (:255-258) on the side stream, from a COPY of its genome: the epoch below may mutate
+            # the champion's own row (elites are protected as clones, mod_neuro_evo.py:494-505)
+            ci = int(np.argmax(pop_fitness))
+            if spec:
+                self.spec_tries += 1
+                self.spec_hits += ci in spec
+            f_champ = spec.get(ci)
+            if f_champ is None:
+                f_champ = self._fly(self.champion, self.validation_tests, trace=bool(args.should_log), stream=self._side, copy_genome=True,
+                                    draws=val_draws)
+            lap('stats')
             elite_index = self.evolver.epoch(self.pop, dev_fitness)
+            lap('epoch')
         # RL half (agent.py:267-281)
         self._collect(self.rl_agent, f_explore, store_transition=True)
+        lap('collect_exploration')
         rl_train_scores = self.train_rl(self.gen_frames)
+        lap('train_rl')
         if f_rlval is None:
             f_rlval = self._fly(self.rl_agent, self.validation_tests, trace=bool(args.should_log))
         rl_reward, rl_std, rl_ep_len, rl_ep_std, rl_episode, rl_sm, rl_sm_sd = self._validation_stats(
             self._collect(self.rl_agent, f_rlval, want_history=bool(args.should_log)))
+        lap('rl_validation')
         if args.pop_size == 0:
             ep_len_avg, ep_len_sd = rl_ep_len, rl_ep_std
         if args.should_log:
@@ -347,6 +380,12 @@ class Agent:
                 replace_index = (replace_index + 1) % len(self.pop)
             self.rl_to_evo(self.rl_agent, self.pop[replace_index])
             self.evolver.rl_policy = replace_index
+        if f_champ is not None:
+            test_score, test_sd, _, _, last_episode, _, _ = self._validation_stats(
+                self._collect(self.champion, f_champ, want_history=bool(args.should_log)))
+            if args.should_log:
+                self.champion_history = last_episode.get_history()
+        lap('champion_validation')
         return {
             'best_train_fitness': best_train_fitness, 'test_score': test_score, 'test_sd': test_sd,
             'pop_avg': population_avg, 'pop_min': worst_train_fitness, 'elite_index': elite_index,
@@ -362,7 +401,7 @@ class Agent:
         st = torch.as_tensor(draw[1][None], device=self.device)
         md = torch.tensor([env.mode_code], dtype=torch.int32, device=self.device)
         f = _Flight()
-        f.levels, f.starts, f.n, f.noise_state, f.stream = [draw[0]], [draw[1]], 1, None, None
+        f.levels, f.starts, f.n, f.noise_state, f.stream, f.keep = [draw[0]], [draw[1]], 1, None, None, None
         f.r = rollout.population_rollout(self._genome_of(agent), self.shape, lv, st, md, trace=True, horizon=self._horizon(),
                                          actions=True, **self._eval_kw())
         f.r.smoothness = rollout.smoothness(f.r.actions, f.r.steps)
@@ -385,6 +424,10 @@ class Agent:
         if self.rl_history is not None:
             np.savetxt(os.path.join(parameters.save_foldername, 'rl_statehistory_episode%d.txt' % self.num_episodes),
                        self.rl_history, header=str(self.num_episodes))
+
+
+def _to_device(a, device):
+    return torch.from_numpy(np.ascontiguousarray(a)).pin_memory().to(device, non_blocking=True)
 
 
 class _ReturnOnly:

@@ -1116,6 +1116,32 @@ static void choose_shape(int pop, int n_envs, int apc_max, int sms, int* apc_out
     }
 }
 
+// Scratch of a launch (genomes in the shared-memory layout + hand-over records): one grow-only buffer per (device,
+// stream), kept for the life of the process.  Launches on one stream are ordered, so they can share it; launches on
+// different streams (the Agent's side-stream episodes next to the population rollout) get their own.  No stream-ordered
+// allocator here: growing its pool maps memory, which waits for kernels in flight on OTHER streams.
+#include <map>
+#include <mutex>
+struct ScratchBuf { void* p; size_t bytes; };
+static std::mutex g_scratch_mu;
+static std::map<std::pair<int, cudaStream_t>, ScratchBuf> g_scratch;
+static cudaError_t scratch_get(cudaStream_t s, size_t bytes, void** out)
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(g_scratch_mu);
+    ScratchBuf& b = g_scratch[std::make_pair(dev, s)];
+    if (b.bytes < bytes) {
+        if (b.p) { cudaStreamSynchronize(s); cudaFree(b.p); b.p = nullptr; b.bytes = 0; }
+        const size_t want = bytes + bytes / 4;
+        cudaError_t e = cudaMalloc(&b.p, want);
+        if (e != cudaSuccess) return e;
+        b.bytes = want;
+    }
+    *out = b.p;
+    return cudaSuccess;
+}
+
 template <int H, bool TABS>
 static cudaError_t launch_persist(RolloutArgs& ar, int apc_max, cudaStream_t s, void** scratch)
 {
@@ -1137,7 +1163,7 @@ static cudaError_t launch_persist(RolloutArgs& ar, int apc_max, cudaStream_t s, 
     const size_t wt_bytes = (size_t)ar.pop * ar.P4 * 4;
     const long long hn = ar.n_tasks > ar.n_slots ? ar.n_slots * wps * 32 : 0;
     const size_t ho_bytes = (size_t)hn * (NX * 8 + 8 + 8 + 7 * 4 + 4) + (size_t)(hn / 32) * 4;
-    cudaError_t e = cudaMallocAsync(scratch, wt_bytes + ho_bytes + 256, s);
+    cudaError_t e = scratch_get(s, wt_bytes + ho_bytes + 512, scratch);
     if (e != cudaSuccess) return e;
     unsigned char* base = (unsigned char*)*scratch;
     float* wt = (float*)base;
@@ -1212,7 +1238,6 @@ static int rollout_impl(const serl_rollout_desc& d, void* stream)
         else if (H == 72) e = launch_persist<72, true>(ar, apc_max, s, &scratch);
         else if (H == 96) e = launch_persist<96, true>(ar, apc_max, s, &scratch);
         else e = tabs ? launch_persist<128, true>(ar, apc_max, s, &scratch) : launch_persist<128, false>(ar, apc_max, s, &scratch);
-        if (scratch) cudaFreeAsync(scratch, s);
     } else {
         const size_t smem = (size_t)ar.P4 * 4 + 2ull * H * 128 * 4;
         if (smem > 227 * 1024) return serl_fail(SERL_ERR_UNSUPPORTED, "serl_rollout: genome + activations exceed 227 KB of shared memory");

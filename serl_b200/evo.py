@@ -46,7 +46,7 @@ def _waves(items, reads, writes):
 
 class EvoPlan:
     __slots__ = ('clone_waves', 'cross_waves', 'mut_seg', 'mut_off', 'mut_kind', 'mut_z', 'elite', 'new_elitists',
-                 'offsprings', 'unselects', 'n_cross_ops', 'timing')
+                 'offsprings', 'unselects', 'n_cross_ops', 'timing', 'elitist_index')
 
 
 def plan_epoch(index_rank, offsprings_raw, table, population_size, num_elitists, mutation_prob, selection=None, native=False):
@@ -83,6 +83,7 @@ def plan_epoch(index_rank, offsprings_raw, table, population_size, num_elitists,
         unselects.append(unselects[random.randrange(len(unselects))])
     plan.elite = new_elitists[0]
     plan.new_elitists, plan.offsprings, plan.unselects = new_elitists, offsprings, unselects
+    plan.elitist_index = [int(i) for i in elitist_index]       # the ranked elites; new_elitists[k] is the protected clone of [k]
     plan.timing = None
     if native:
         return _plan_tail_native(plan, table, index_rank[num_elitists:], mutation_prob)
