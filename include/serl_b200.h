@@ -91,6 +91,11 @@ int serl_rollout_eval(const float* d_weights, int32_t pop, const serl_actor_shap
  *                envs/phlabenv.py:369-375 -> critical buffer); rows past the episode's length are not written
  *   d_status     optional int32 word the kernel ORs error bits into (SERL_STATUS_*); the caller zeroes it and reads it
  *                after synchronising
+ *   widths       HOST pointer to n_widths hidden-layer widths, or NULL.  n_widths == 0: the reference's uniform actor described
+ *                by `shape` (K1, warp-GEMV on CUDA cores).  n_widths == 2: the two-hidden-layer generalisation
+ *                Linear(7,w1) act Linear(w1,w2) LayerNorm act Linear(w2,3) tanh (BASELINE config 5: [400,300], [128,128]);
+ *                genome = parameters() order, serl_actor_num_params_wide floats per actor; only shape.activation is read
+ *                from `shape`; layer 2 runs on the tensor cores (tcgen05, 3xTF32) with TMA-streamed weight slabs
  *   sm_limit     > 0: use at most that many SMs (CTAs of the persistent kernel) — leaves room for small launches that run
  *                concurrently on other streams (the RL / validation episodes of Agent.train); 0 = all SMs
  * t_max <= 0 selects the training defaults (20 s, smooth width 3 s). */
@@ -106,6 +111,7 @@ typedef struct {
     float* d_replay; int32_t replay_env;
     int32_t* d_status;
     int32_t sm_limit;
+    const int32_t* widths; int32_t n_widths;
 } serl_rollout_desc;
 int serl_rollout_run(const serl_rollout_desc* desc, void* stream);
 
@@ -114,6 +120,11 @@ int serl_rollout_run(const serl_rollout_desc* desc, void* stream);
  * rollout kernel's, bit for bit. */
 int serl_actor_forward(const float* d_genome, const serl_actor_shape* shape, const float* d_obs, int32_t n,
                        float* d_actions, void* stream);
+
+/* Wide (width-list) actors: parameter count, and Actor.forward for a batch through the tensor-core device code. */
+int64_t serl_actor_num_params_wide(const int32_t* widths, int32_t n_widths);
+int serl_actor_forward_wide(const float* d_genome, const int32_t* widths, int32_t n_widths, int32_t activation,
+                            const float* d_obs, int32_t n, float* d_actions, void* stream);
 
 /* K6: action smoothness of n_traj trajectories (base/core/utils.py:82-120 calc_smoothness; agent.py:128-134):
  * out[t] = -sqrt(sum_i sum_k f_k |FFT(y_i)[k]|^2 dt 2/N) * 100 * 80/(N dt) over the N = d_steps[t] executed steps of

@@ -75,3 +75,38 @@ def from_state_dict(sd, activation):
     a = Actor(state_dim, action_dim, hidden, len(lin) - 2, activation)
     a.load_state_dict(sd)
     return a
+
+
+class WideActor(nn.Module):
+    """Width-list generalisation used by BASELINE config 5 ([400,300], [128,128]): Linear(S,w1), act,
+    {Linear(w_i,w_{i+1}), LayerNorm, act} ..., Linear(w_n,A), Tanh — the reference's Actor is the case of equal widths."""
+
+    def __init__(self, widths, state_dim=7, action_dim=3, activation='tanh'):
+        super().__init__()
+        layers = [nn.Linear(state_dim, widths[0]), _act(activation)]
+        for a, b in zip(widths[:-1], widths[1:]):
+            layers.extend([nn.Linear(a, b), LayerNorm(b), _act(activation)])
+        layers.extend([nn.Linear(widths[-1], action_dim), nn.Tanh()])
+        self.net = nn.Sequential(*layers)
+
+    def forward(self, x):
+        return self.net(x)
+
+
+def num_params_wide(widths, state_dim=7, action_dim=3):
+    n = state_dim * widths[0] + widths[0]
+    for a, b in zip(widths[:-1], widths[1:]):
+        n += a * b + 3 * b
+    return n + widths[-1] * action_dim + action_dim
+
+
+def unflatten_wide(vec, widths, activation='tanh'):
+    a = WideActor(widths, activation=activation)
+    off = 0
+    v = torch.as_tensor(np.asarray(vec, dtype=np.float32))
+    for p in a.parameters():
+        n = p.numel()
+        p.data.copy_(v[off:off + n].reshape(p.shape))
+        off += n
+    assert off == v.numel()
+    return a

@@ -64,3 +64,23 @@ def expm1_neg_kernel_order(x):
     y = np.empty_like(x)
     lib.ko_expm1f_neg_batch(x.ctypes.data_as(ctypes.c_void_p), x.size, y.ctypes.data_as(ctypes.c_void_p))
     return y
+
+
+def evaluate_population_wide(genomes, widths, levels, starts, modes, activation='tanh', t_max=20.0, smooth_w=3.0, horizon=2001, threads=None):
+    """width-list actors ([w1, w2, ...]) through the C episode port (index-order float32 forward pass)."""
+    if threads:
+        os.environ['OMP_NUM_THREADS'] = str(int(threads))
+    lib = ctypes.CDLL(_build.build())
+    lib.oracle_population_wide.restype = ctypes.c_long
+    g = np.ascontiguousarray(genomes, dtype=np.float32)
+    lv = np.ascontiguousarray(levels, dtype=np.float64)
+    st = np.ascontiguousarray(starts, dtype=np.float64)
+    md = np.asarray([mode_code(m) for m in modes], dtype=np.int32)
+    w = np.asarray(widths, dtype=np.int32)
+    pop, n_envs = g.shape[0], md.shape[0]
+    ret = np.zeros((pop, n_envs))
+    stp = np.zeros((pop, n_envs), dtype=np.int32)
+    vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    lib.oracle_population_wide(vp(g), pop, g.shape[1], vp(w), len(w), _ACT[activation], vp(md), vp(lv), vp(st), n_envs,
+                               ctypes.c_double(t_max), ctypes.c_double(smooth_w), int(horizon), vp(ret), vp(stp))
+    return ret, stp

@@ -50,6 +50,45 @@ static void actor_forward(const float* p, int S, int A, int H, int L, int act, c
     }
 }
 
+/* width-list generalisation (BASELINE config 5): Linear(S,w0) act {Linear(w_i,w_i+1) LayerNorm act} Linear(w_n,A) tanh */
+static void actor_forward_wide(const float* p, int S, int A, const int* widths, int nw, int act, const float* obs, float* action)
+{
+    float a[1024], b[1024];
+    int H = widths[0];
+    for (int j = 0; j < H; ++j) {
+        float acc = 0.f;
+        for (int i = 0; i < S; ++i) acc += p[j * S + i] * obs[i];
+        a[j] = act_fn(act, acc + p[H * S + j]);
+    }
+    p += H * S + H;
+    for (int l = 1; l < nw; ++l) {
+        const int Hi = widths[l - 1], Ho = widths[l];
+        const float *W = p, *bias = p + Ho * Hi, *gamma = bias + Ho, *beta = gamma + Ho;
+        float sum = 0.f;
+        for (int j = 0; j < Ho; ++j) {
+            float acc = 0.f;
+            for (int i = 0; i < Hi; ++i) acc += W[j * Hi + i] * a[i];
+            b[j] = acc + bias[j];
+            sum += b[j];
+        }
+        const float mean = sum / (float)Ho;
+        float ss = 0.f;
+        for (int j = 0; j < Ho; ++j) ss += (b[j] - mean) * (b[j] - mean);
+        const float den = sqrtf(ss / (float)(Ho - 1)) + 1e-6f;
+        for (int j = 0; j < Ho; ++j) a[j] = act_fn(act, gamma[j] * (b[j] - mean) / den + beta[j]);
+        p += Ho * Hi + 3 * Ho;
+        H = Ho;
+    }
+    for (int j = 0; j < A; ++j) {
+        float acc = 0.f;
+        for (int i = 0; i < H; ++i) acc += p[j * H + i] * a[i];
+        action[j] = tanhf(acc + p[A * H + j]);
+    }
+}
+
+static const int* g_widths = 0;      /* set by oracle_population_wide for the duration of a call */
+static int g_nw = 0;
+
 static double ref_deg(const double* lv, const double* st, double t, double offset, double smooth_w)
 {
     int k = 0;
@@ -94,7 +133,8 @@ double oracle_episode(const float* genome, int S, int A, int H, int L, int act, 
     int k = 0;
     for (; k < horizon;) {
         float a[3];
-        if (actor_order == 1) ko_actor_forward(genome, S, A, H, L, act, obs, a);
+        if (actor_order == 2) actor_forward_wide(genome, S, A, g_widths, g_nw, act, obs, a);
+        else if (actor_order == 1) ko_actor_forward(genome, S, A, H, L, act, obs, a);
         else actor_forward(genome, S, A, H, L, act, obs, a);
         for (int i = 0; i < 3; ++i) {
             const float t1 = a[i] + 1.0f;
@@ -137,4 +177,13 @@ long oracle_population(const float* genomes, int pop, int P, int S, int A, int H
         total += steps[j];
     }
     return total;
+}
+
+/* the same for width-list actors (actor_order 2: index-order float32 sums + libm tanh) */
+long oracle_population_wide(const float* genomes, int pop, int P, const int* widths, int nw, int act, const int* modes,
+                            const double* levels, const double* starts, int n_envs, double t_max, double smooth_w, int horizon,
+                            double* returns, int* steps)
+{
+    g_widths = widths; g_nw = nw;
+    return oracle_population(genomes, pop, P, 7, 3, widths[0], 0, act, modes, levels, starts, n_envs, t_max, smooth_w, horizon, returns, steps, 2);
 }

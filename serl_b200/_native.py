@@ -22,7 +22,8 @@ class RolloutDesc(ctypes.Structure):
                 ('d_trace', ctypes.c_void_p), ('d_actions', ctypes.c_void_p),
                 ('t_max', ctypes.c_double), ('smooth_width', ctypes.c_double),
                 ('d_env_order', ctypes.c_void_p), ('d_replay', ctypes.c_void_p), ('replay_env', ctypes.c_int32),
-                ('d_status', ctypes.c_void_p), ('sm_limit', ctypes.c_int32)]
+                ('d_status', ctypes.c_void_p), ('sm_limit', ctypes.c_int32),
+                ('widths', ctypes.c_void_p), ('n_widths', ctypes.c_int32)]
 
 
 REPLAY_COLS = 20
@@ -53,6 +54,10 @@ def lib():
         L.serl_rollout_run.argtypes = [ctypes.POINTER(RolloutDesc), vp]
         L.serl_actor_forward.restype = ctypes.c_int
         L.serl_actor_forward.argtypes = [vp, ctypes.POINTER(ActorShape), vp, i32, vp, vp]
+        L.serl_actor_num_params_wide.restype = i64
+        L.serl_actor_num_params_wide.argtypes = [vp, i32]
+        L.serl_actor_forward_wide.restype = ctypes.c_int
+        L.serl_actor_forward_wide.argtypes = [vp, vp, i32, i32, vp, i32, vp, vp]
         L.serl_smoothness.restype = ctypes.c_int
         L.serl_smoothness.argtypes = [vp, vp, i32, i32, ctypes.c_double, vp, vp]
         L.serl_launch_count.restype = i64

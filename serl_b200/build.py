@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libserl_b200.so')
-SOURCES = ['common.cu', 'rollout.cu', 'evo.cu', 'evo_plan.cpp']
+SOURCES = ['common.cu', 'rollout.cu', 'rollout_tc.cu', 'evo.cu', 'evo_plan.cpp']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xptxas', '-v']
 
@@ -40,10 +40,15 @@ def _build(LIB, extra, bdir, force, verbose):
     objs = []
     os.makedirs(os.path.join(HERE, bdir), exist_ok=True)
     log = []
-    for src in SOURCES:
+    from concurrent.futures import ThreadPoolExecutor
+
+    def compile_one(src):
         obj = os.path.join(HERE, bdir, src.replace('.cu', '.o').replace('.cpp', '.o'))
         cmd = [nvcc] + NVCC_FLAGS + extra + ['-c', os.path.join(CSRC, src), '-o', obj]
-        r = subprocess.run(cmd, capture_output=True, text=True)
+        return src, obj, subprocess.run(cmd, capture_output=True, text=True)
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:          # the translation units are independent
+        results = list(ex.map(compile_one, SOURCES))
+    for src, obj, r in results:
         log.append(r.stderr)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)

@@ -65,17 +65,19 @@ def variant_sorted_order(env_mode):
 
 def population_rollout(weights, shape, ref_levels, ref_starts, env_mode, horizon=HORIZON, trace=False, out=None, action_noise=None,
                        actions=False, t_max=None, smooth_width=None, env_order=None, replay_env=None, status=True, sm_limit=0,
-                       fitness=True):
+                       fitness=True, widths=None):
     """weights [pop,P] fp32 cuda; ref_levels/ref_starts [n_envs,2,6] f64 cuda; env_mode [n_envs] int32 cuda.
     env_order: optional int32 [n_envs] permutation (see variant_sorted_order); replay_env: record the transitions of that env
     of every actor into result.replay [pop, horizon, REPLAY_COLS]; status: carry the device status word (result.check());
-    sm_limit: SMs this launch may occupy (0 = all); fitness=False skips the per-actor mean kernel."""
+    sm_limit: SMs this launch may occupy (0 = all); fitness=False skips the per-actor mean kernel.
+    widths=[w1, w2]: wide two-hidden-layer actors on the tensor-core kernel (csrc/rollout_tc.cu); `shape` then only supplies the
+    activation."""
     if not weights.is_cuda:
         raise _native.NativeError('population_rollout needs CUDA tensors (no CPU fallback)')
     L = _native.lib()
     pop, P = weights.shape
     assert weights.dtype == torch.float32 and weights.is_contiguous()
-    assert P == num_params(shape), (P, num_params(shape))
+    assert P == (num_params_wide(widths) if widths else num_params(shape)), (P, widths)
     n_envs = env_mode.shape[0]
     assert ref_levels.shape == (n_envs, 2, 6) and ref_levels.dtype == torch.float64 and ref_levels.is_contiguous()
     assert ref_starts.shape == (n_envs, 2, 6) and ref_starts.dtype == torch.float64 and ref_starts.is_contiguous()
@@ -115,8 +117,30 @@ def population_rollout(weights, shape, ref_levels, ref_starts, env_mode, horizon
     if sm_limit < 0:         # leave -sm_limit SMs to concurrent small launches
         sm_limit = max(1, torch.cuda.get_device_properties(dev).multi_processor_count + int(sm_limit))
     d.sm_limit = int(sm_limit)
+    if widths:
+        warr = (ctypes.c_int32 * len(widths))(*[int(x) for x in widths])
+        d.widths, d.n_widths = ctypes.cast(warr, ctypes.c_void_p), len(widths)
     _native.check(L.serl_rollout_run(ctypes.byref(d), stream), 'serl_rollout_run')
     return r
+
+
+def num_params_wide(widths):
+    arr = (ctypes.c_int32 * len(widths))(*[int(x) for x in widths])
+    return int(_native.lib().serl_actor_num_params_wide(arr, len(widths)))
+
+
+def actor_forward_wide(genome, widths, activation, obs):
+    """forward pass of a wide [w1, w2] actor for a batch of observations through the tensor-core device code (tcgen05 3xTF32)."""
+    if not genome.is_cuda:
+        raise _native.NativeError('actor_forward_wide needs CUDA tensors (no CPU fallback)')
+    assert genome.dtype == torch.float32 and genome.is_contiguous() and genome.numel() == num_params_wide(widths)
+    assert obs.dtype == torch.float32 and obs.is_contiguous() and obs.shape[1] == 7
+    out = torch.empty((obs.shape[0], 3), dtype=torch.float32, device=genome.device)
+    arr = (ctypes.c_int32 * len(widths))(*[int(x) for x in widths])
+    stream = ctypes.c_void_p(torch.cuda.current_stream(genome.device).cuda_stream)
+    _native.check(_native.lib().serl_actor_forward_wide(_ptr(genome), arr, len(widths), _native.ACTIVATIONS[activation.lower()], _ptr(obs),
+                                                        obs.shape[0], _ptr(out), stream), 'serl_actor_forward_wide')
+    return out
 
 
 def actor_forward(genome, shape, obs):
