@@ -476,6 +476,10 @@ def run_ours(args):
 
 
 def main():
+    # exactly ONE line on stdout (the JSON): libraries that print there (NCCL's version banner) are sent to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, 'w')
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=3)
