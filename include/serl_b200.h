@@ -96,6 +96,9 @@ int serl_rollout_eval(const float* d_weights, int32_t pop, const serl_actor_shap
  *                Linear(7,w1) act Linear(w1,w2) LayerNorm act Linear(w2,3) tanh (BASELINE config 5: [400,300], [128,128]);
  *                genome = parameters() order, serl_actor_num_params_wide floats per actor; only shape.activation is read
  *                from `shape`; layer 2 runs on the tensor cores (tcgen05, 3xTF32) with TMA-streamed weight slabs
+ *   d_sensor_noise optional [pop, n_envs, horizon + 1, 7] fp32 standard-normal draws: the sensor-noise shim of
+ *                envs/noise/citation.py:72-82 (mode 'noise'; also the outputs of envs/gust) applied to every native step
+ *                output — row 0 for reset()'s step, row k + 1 for env step k; order p,q,r, alpha, beta, phi, theta
  *   sm_limit     > 0: use at most that many SMs (CTAs of the persistent kernel) — leaves room for small launches that run
  *                concurrently on other streams (the RL / validation episodes of Agent.train); 0 = all SMs
  * t_max <= 0 selects the training defaults (20 s, smooth width 3 s). */
@@ -112,6 +115,7 @@ typedef struct {
     int32_t* d_status;
     int32_t sm_limit;
     const int32_t* widths; int32_t n_widths;
+    const float* d_sensor_noise;
 } serl_rollout_desc;
 int serl_rollout_run(const serl_rollout_desc* desc, void* stream);
 

@@ -39,11 +39,21 @@ class CitationEnv:
         cmd = np.pad(u, (0, 7), 'constant', constant_values=(0.))
         cmd = P.apply_fault(self.fault, cmd)
         out, self.X = self.plant.step(self.X, cmd)
+        z = getattr(self, 'noise_z', None)
+        if z is not None:                      # sensor-noise shim envs/noise/citation.py:72-82 with GIVEN standard-normal draws
+            zz = z[self._call]
+            out = np.array(out, dtype=np.float64)
+            out[:3] += 3.0 * 10**(-5) + 6.3 * 10**(-4) * zz[0:3]
+            out[4] += 4.0 * 10**(-10) * zz[3]
+            out[5] += 1.8 * 10**(-3) + 2.7 * 10**(-4) * zz[4]
+            out[6:8] += 4.0 * 10**(-3) + 3.2 * 10**(-5) * zz[5:7]
+        self._call = getattr(self, '_call', 0) + 1
         return out
 
     # phlabenv.py:401-428
     def reset(self, levels=None, starts=None):
         self.t = 0.
+        self._call = 0
         self.X = self.plant.initial_state()
         self.last_u = np.zeros(3)
         self.x = self._native_step(self.last_u)

@@ -40,6 +40,15 @@ def calc_smoothness(y: np.ndarray, dt: float = 0.01, **kwargs) -> float:
     return -(np.sqrt(roughness_per_channel.sum()) * 100 * (80 / (n_samples * dt)))
 
 
+def calc_nMAE(error: np.ndarray) -> float:
+    """Normalised mean absolute tracking error in % (base/core/utils.py:39-58): per-channel mean |error| over ranges of 20 deg
+    for theta and phi and max(|mean beta error|, 3.14159/180) for beta, averaged over the three channels."""
+    err = np.asarray(error, dtype=np.float64)
+    mae = np.abs(err).mean(axis=0)
+    ranges = np.array([np.deg2rad(20), np.deg2rad(20), max(abs(err[:, -1].mean()), 3.14159 / 180)])
+    return float(np.mean(mae / ranges) * 100)
+
+
 def load_config(model_path: str, verbose: bool = False) -> dict:
     """Read `<run>/files/config.yaml` as written by wandb ({key: {value: v, desc: ...}}) into a flat dict."""
     import yaml

@@ -113,6 +113,10 @@ extern "C" int serl_ssne_select(const double* d_fitness, int32_t pop, const int3
 {
     if (!d_fitness || !d_index_rank || (n_off > 0 && (!d_draws || !d_offsprings_raw))) return serl_fail(SERL_ERR_ARG, "serl_ssne_select: null pointer");
     if (pop <= 0 || pop > 16384 || n_off < 0) return serl_fail(SERL_ERR_ARG, "serl_ssne_select: 0 < pop <= 16384 required");
+    if (pop * sizeof(int) > 48 * 1024) {        // above the default dynamic shared-memory limit: opt in
+        cudaError_t ea = cudaFuncSetAttribute(ssne_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(pop * sizeof(int)));
+        if (ea != cudaSuccess) return serl_fail_cuda(ea, "cudaFuncSetAttribute(ssne_select)");
+    }
     ssne_select_kernel<<<1, 1024, pop * sizeof(int), (cudaStream_t)stream>>>(d_fitness, pop, d_draws, n_off, d_index_rank, d_offsprings_raw);
     serl_count_launch();
     cudaError_t e = cudaGetLastError();

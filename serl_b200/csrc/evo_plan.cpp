@@ -58,8 +58,9 @@ struct PyRandom {
     MT g;
     bool has_gauss;
     double gauss_next;
-    uint32_t randbelow(uint32_t n)   // Random._randbelow_with_getrandbits, n >= 1
+    uint32_t randbelow(uint32_t n)   // Random._randbelow_with_getrandbits, n >= 1 (n == 0 is rejected by serl_plan_create)
     {
+        if (n == 0) return 0;
         int k = 0;
         for (uint32_t v = n; v; v >>= 1) ++k;      // n.bit_length()
         uint32_t r = g.next() >> (32 - k);
@@ -109,6 +110,9 @@ void* serl_plan_create(uint32_t* py_state, double* py_gauss, uint32_t* np_state,
                        const int32_t* offsprings, int32_t n_offsprings,
                        const int32_t* mut_order, int32_t n_mut, double mutation_prob)
 {
+    // random.choice([]) raises IndexError in the reference (mod_neuro_evo.py:519-520); an empty choice pool next to a
+    // non-empty crossover list is reported as a failed plan (NULL) instead of spinning in randbelow(0)
+    if (n_unselects >= 2 && (n_new_elitists <= 0 || n_offsprings <= 0)) return nullptr;
     PyRandom R;
     memcpy(R.g.mt, py_state, 624 * sizeof(uint32_t));
     R.g.idx = (int)py_state[624];

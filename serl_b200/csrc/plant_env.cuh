@@ -270,6 +270,7 @@ struct RolloutArgs {
     float* replay; int replay_env;  // optional [pop, horizon, SERL_REPLAY_COLS] transitions of one env per actor
     int* status;                    // optional device status word
     int sm_limit;                   // > 0: CTAs of the persistent kernel (SMs) this launch may use
+    const float* sensor_noise;      // optional [pop, n_envs, horizon + 1, 7] standard-normal draws of the sensor-noise shim
     // persistent schedule
     const float* wt;                // [pop][P4] genomes in the shared-memory layout (transposed matrices), 16-byte aligned rows
     int P4;                         // row stride of wt / smem slot size in floats (multiple of 4)
@@ -315,14 +316,34 @@ __device__ __forceinline__ void env_bind(Env& e, const RolloutArgs& a, int env, 
     e.theta_trim = plant_ic(variant)[7] * RAD2DEG;
 }
 
+// sensor-noise shim (envs/noise/citation.py:72-82, same model in envs/gust): every native step() output gets
+// p,q,r += 3e-5 + 6.3e-4 z; alpha += 4e-10 z; beta += 1.8e-3 + 2.7e-4 z; phi,theta += 4e-3 + 3.2e-5 z  (7 draws per call,
+// in that order); the plant's own state is not touched.  call = 0 for reset()'s step, k + 1 for env step k.
+__device__ __forceinline__ void sensor_noise(const RolloutArgs& a, size_t traj, int call, double* x)
+{
+    if (!a.sensor_noise) return;
+    const float* z = a.sensor_noise + (traj * (size_t)(a.horizon + 1) + call) * 7;
+    x[0] += 3.0 * 1e-5 + 6.3 * 1e-4 * (double)z[0];
+    x[1] += 3.0 * 1e-5 + 6.3 * 1e-4 * (double)z[1];
+    x[2] += 3.0 * 1e-5 + 6.3 * 1e-4 * (double)z[2];
+    x[4] += 4.0 * 1e-10 * (double)z[3];
+    x[5] += 1.8 * 1e-3 + 2.7 * 1e-4 * (double)z[4];
+    x[6] += 4.0 * 1e-3 + 3.2 * 1e-5 * (double)z[5];
+    x[7] += 4.0 * 1e-3 + 3.2 * 1e-5 * (double)z[6];
+}
+
 // reset(): initialize(), one zero-command step returns the initial state (phlabenv.py:401-428). obs = [0,0,0,p,q,r,alpha]
-static __device__ void env_reset(Env& e, const RolloutArgs& a, int env, float* obs)
+static __device__ void env_reset(Env& e, const RolloutArgs& a, int env, float* obs, size_t traj = 0)
 {
     const double* ic = plant_ic(a.env_mode[env] & 0xff);
 #pragma unroll
     for (int i = 0; i < NX; ++i) e.X[i] = ic[i];
+    double x0[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x0[i] = e.X[i];
+    sensor_noise(a, traj, 0, x0);
     obs[0] = obs[1] = obs[2] = 0.f;
-    obs[3] = (float)e.X[0]; obs[4] = (float)e.X[1]; obs[5] = (float)e.X[2]; obs[6] = (float)e.X[4];
+    obs[3] = (float)x0[0]; obs[4] = (float)x0[1]; obs[5] = (float)x0[2]; obs[6] = (float)x0[4];
     double U[3] = {0.0, 0.0, 0.0}, cmd[3];
     apply_fault(e.fault, U, cmd);
     plant_step(e.pv, e.X, cmd, e.tab, a.trace != nullptr);
@@ -362,6 +383,7 @@ static __device__ void env_step(Env& e, const RolloutArgs& ar, size_t traj, int 
 #pragma unroll
     for (int i = 0; i < 12; ++i) xo[i] = e.X[i];
     plant_step(e.pv, e.X, cmd, e.tab, ar.trace != nullptr);
+    sensor_noise(ar, traj, e.k + 1, xo);
 
     const double t = e.t;
     // + signals.Const(0., t_max, theta_trim) (phlabenv.py:344): the trim offset exists on [0, t_max] only

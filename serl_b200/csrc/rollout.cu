@@ -386,7 +386,7 @@ rollout_kernel_persist(RolloutArgs ar)
                 const int kk = __ldcg(ar.ho.k + hx);
                 e.k = kk & 0x3fffffff; e.done = ((kk >> 30) & 1) != 0;
             } else {
-                env_reset(e, ar, env, obs);
+                env_reset(e, ar, env, obs, (size_t)actor * ar.n_envs + env);
             }
         } else {
             e.done = true; e.k = 0; e.ret = 0.0; e.t = 0.0; e.fault = 0; e.pv = pv_base; e.theta_trim = 0.0;
@@ -446,7 +446,7 @@ rollout_kernel_simple(RolloutArgs ar)
     e.tab = plant_tables_blob;
     float obs[7], a[3];
     env_bind(e, ar, env, &plant_pv[0][0]);
-    env_reset(e, ar, env, obs);
+    env_reset(e, ar, env, obs, (size_t)actor * ar.n_envs + env);
     const size_t traj = (size_t)actor * ar.n_envs + env;
     const bool replay = ar.replay != nullptr && env == ar.replay_env;
     while (!e.done) {
@@ -785,7 +785,7 @@ static int rollout_impl(const serl_rollout_desc& d, void* stream)
     ar.pop = d.pop;
     ar.t_max = d.t_max > 0.0 ? d.t_max : 20.0;
     ar.smooth_w = d.t_max > 0.0 ? d.smooth_width : 3.0;
-    ar.env_order = d.d_env_order; ar.replay = d.d_replay; ar.replay_env = d.replay_env; ar.status = d.d_status; ar.sm_limit = d.sm_limit;
+    ar.env_order = d.d_env_order; ar.replay = d.d_replay; ar.replay_env = d.replay_env; ar.status = d.d_status; ar.sm_limit = d.sm_limit; ar.sensor_noise = d.d_sensor_noise;
     ar.P4 = (ar.P + 3) & ~3;
     const int H = shape->hidden;
     cudaError_t e;

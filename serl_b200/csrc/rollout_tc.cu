@@ -355,7 +355,7 @@ rollout_kernel_tc(TcArgs ar)
         float obs[7], a[3];
         if (valid) {
             env_bind(e, r, env, &plant_pv[0][0]);
-            env_reset(e, r, env, obs);
+            env_reset(e, r, env, obs, (size_t)actor * r.n_envs + env);
         } else {
             e.done = true; e.k = 0; e.ret = 0.0; e.t = 0.0; e.fault = 0; e.pv = &plant_pv[0][0]; e.theta_trim = 0.0;
             e.ref_lv = r.ref_levels; e.ref_st = r.ref_starts;
@@ -478,7 +478,7 @@ int rollout_tc_impl(const serl_rollout_desc& d, const int32_t* widths, int n_wid
     r.action_noise = d.d_action_noise; r.returns = d.d_returns; r.steps = d.d_steps; r.actions = d.d_actions; r.pop = d.pop;
     r.t_max = d.t_max > 0.0 ? d.t_max : 20.0;
     r.smooth_w = d.t_max > 0.0 ? d.smooth_width : 3.0;
-    r.env_order = d.d_env_order; r.replay = d.d_replay; r.replay_env = d.replay_env; r.status = d.d_status;
+    r.env_order = d.d_env_order; r.replay = d.d_replay; r.replay_env = d.replay_env; r.status = d.d_status; r.sensor_noise = d.d_sensor_noise;
     size_t smem = 0;
     int rc = tc_prepare(ar, d.d_weights, d.pop, widths, n_widths, s, &smem);
     if (rc != SERL_OK) return rc;

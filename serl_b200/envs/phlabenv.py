@@ -49,6 +49,12 @@ class CitationEnv:
             m = 'nominal'
         alias = {'high-q': 'h2000-v150', 'low-q': 'h10000-v90', 'cg-aft': 'cg'}
         m = alias.get(m, m)
+        # 'noise' (envs/phlabenv.py:139-142): the nominal plant behind the sensor-noise shim (envs/noise/citation.py:72-82)
+        self.sensor_noise = m == 'noise'
+        if self.sensor_noise:
+            m = 'nominal'
+        if m in ('gust', 'cg-timed', 'cg-shift', 'test'):
+            raise ValueError("mode '%s': the time-triggered plant builds (gust / cg_timed / test) are not lifted (DESIGN.md: out of scope)" % m)
         if m not in rollout.MODES:
             raise ValueError('Unknown trim condition or control mode!')
         self.mode = m
@@ -130,9 +136,17 @@ class CitationEnv:
         return levels, starts
 
     def init_ref(self, **kwargs):
-        self.levels, self.starts = self.draw_reference()
         self.theta_trim = np.rad2deg(self.x[7])
         sw = refsig.widths(self.t_max)[1]
+        self.user_smooth_width = None
+        if 'user_refs' in kwargs:
+            # envs/phlabenv.py:336-341: evaluation references built by the caller (base/evaluate.py:169-180:
+            # signals.SmoothedStepSequence(times, amplitudes, smooth_width=t_max//10)); ours carry their block parameters
+            th, ph = kwargs['user_refs']['theta_ref'], kwargs['user_refs']['phi_ref']
+            self.levels, self.starts = np.stack([th.levels, ph.levels]), np.stack([th.starts, ph.starts])
+            sw = self.user_smooth_width = float(th.smooth_width)
+        else:
+            self.levels, self.starts = self.draw_reference()
         self.ref = [_RefSignal(self.levels[0], self.starts[0], self.theta_trim, sw, self.t_max),
                     _RefSignal(self.levels[1], self.starts[1], 0.0, sw), lambda t: 0.0]
 
@@ -153,6 +167,11 @@ class CitationEnv:
         elif self.fault == 'se':
             b = np.deg2rad(2.5); cmd[0] = np.clip(cmd[0], -b, b)
         x = self._X.cpu().numpy()[0, :12].copy()
+        if self.sensor_noise:                 # envs/noise/citation.py:72-82, same draw order
+            x[:3] += 3.0 * 10**(-5) + 6.3 * 10**(-4) * np.random.randn(3)
+            x[4] += 4.0 * 10**(-10) * np.random.randn(1)[0]
+            x[5] += 1.8 * 10**(-3) + 2.7 * 10**(-4) * np.random.randn(1)[0]
+            x[6:8] += 4.0 * 10**(-3) + 3.2 * 10**(-5) * np.random.randn(2)
         dcmd = torch.as_tensor(cmd[:3].reshape(1, 3), device=self._X.device)
         self._plant('serl_plant_step', ctypes.c_void_p(self._X.data_ptr()), ctypes.c_void_p(dcmd.data_ptr()),
                     ctypes.c_void_p(self._variant.data_ptr()), 1)

@@ -152,6 +152,9 @@ def _plan_tail_native(plan, table, mut_order, mutation_prob):
     L.serl_plan_create.restype = ctypes.c_void_p
     h = L.serl_plan_create(vp(py_state), vp(py_gauss), vp(np_state), vp(tab), tab.shape[0], vp(uns), uns.shape[0],
                            vp(ne), ne.shape[0], vp(offs), offs.shape[0], vp(mo), mo.shape[0], ctypes.c_double(mutation_prob))
+    if not h:
+        raise IndexError('SSNE.epoch: empty choice pool (no new elitists / offsprings) with crossover pairs pending, as '
+                         'random.choice([]) in base/core/mod_neuro_evo.py:519-520')
     h = ctypes.c_void_p(h)
     sizes = np.zeros(5, dtype=np.int64)
     L.serl_plan_sizes(h, vp(sizes))

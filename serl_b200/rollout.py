@@ -65,7 +65,7 @@ def variant_sorted_order(env_mode):
 
 def population_rollout(weights, shape, ref_levels, ref_starts, env_mode, horizon=HORIZON, trace=False, out=None, action_noise=None,
                        actions=False, t_max=None, smooth_width=None, env_order=None, replay_env=None, status=True, sm_limit=0,
-                       fitness=True, widths=None):
+                       fitness=True, widths=None, sensor_noise=None):
     """weights [pop,P] fp32 cuda; ref_levels/ref_starts [n_envs,2,6] f64 cuda; env_mode [n_envs] int32 cuda.
     env_order: optional int32 [n_envs] permutation (see variant_sorted_order); replay_env: record the transitions of that env
     of every actor into result.replay [pop, horizon, REPLAY_COLS]; status: carry the device status word (result.check());
@@ -117,6 +117,9 @@ def population_rollout(weights, shape, ref_levels, ref_starts, env_mode, horizon
     if sm_limit < 0:         # leave -sm_limit SMs to concurrent small launches
         sm_limit = max(1, torch.cuda.get_device_properties(dev).multi_processor_count + int(sm_limit))
     d.sm_limit = int(sm_limit)
+    if sensor_noise is not None:      # envs/noise/citation.py:72-82: standard-normal draws [pop, n_envs, horizon + 1, 7]
+        assert sensor_noise.shape == (pop, n_envs, horizon + 1, 7) and sensor_noise.dtype == torch.float32 and sensor_noise.is_contiguous()
+        d.d_sensor_noise = p(sensor_noise)
     if widths:
         warr = (ctypes.c_int32 * len(widths))(*[int(x) for x in widths])
         d.widths, d.n_widths = ctypes.cast(warr, ctypes.c_void_p), len(widths)

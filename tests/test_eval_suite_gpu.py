@@ -1,0 +1,104 @@
+"""SURVEY.md 8(f) N4 — the evaluation suite on the device: 80 s episodes on user-defined references
+(base/evaluate.py:169-180), the sensor-noise shim (envs/noise/citation.py:72-82), nMAE (base/core/utils.py:39-58)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import actor as A, phlab, refsig
+
+pytestmark = pytest.mark.gpu
+ACT = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'actors.npz'))
+
+
+class KOActor:
+    """the kernel-order actor (bit-exact with the GPU) with the select_action interface of the oracle env loop"""
+
+    def __init__(self, g, hidden=72):
+        self.g, self.hidden = g, hidden
+
+    def select_action(self, obs):
+        from oracle import fast
+        return fast.actor_forward_kernel_order(self.g, np.asarray(obs, dtype=np.float32).reshape(1, 7), self.hidden)[0]
+
+
+def test_sensor_noise_shim_matches_the_oracle_with_the_same_draws():
+    from serl_b200 import rollout
+    dev = torch.device('cuda:0')
+    g = ACT['serl10_elite_h72_tanh']
+    lv, st = refsig.make_ref_params(2, seed_base=31)
+    horizon = 400
+    z = np.random.RandomState(4).randn(1, 2, horizon + 1, 7).astype(np.float32)
+    md = torch.zeros(2, dtype=torch.int32, device=dev)
+    r = rollout.population_rollout(torch.as_tensor(g[None], device=dev), rollout.actor_shape(72), torch.as_tensor(lv, device=dev),
+                                   torch.as_tensor(st, device=dev), md, horizon=horizon, trace=True, sensor_noise=torch.as_tensor(z, device=dev))
+    torch.cuda.synchronize()
+    clean = rollout.population_rollout(torch.as_tensor(g[None], device=dev), rollout.actor_shape(72), torch.as_tensor(lv, device=dev),
+                                       torch.as_tensor(st, device=dev), md, horizon=horizon)
+    for e in range(2):
+        env = phlab.CitationEnv('nominal', 'auto')
+        env.noise_z = z[0, e].astype(np.float64)
+        obs = env.reset(lv[e], st[e])
+        tot = 0.0
+        xs = []
+        for k in range(horizon):
+            obs, rew, done, info = env.step(KOActor(g).select_action(obs))
+            xs.append(env.x.copy())
+            tot += rew
+            if done:
+                break
+        assert int(r.steps[0, e]) == k + 1
+        assert abs(float(r.returns[0, e]) - tot) <= 1e-6 * abs(tot)
+        assert np.abs(r.trace_x[0, e, :k + 1].cpu().numpy()[:, :8] - np.asarray(xs)[:, :8]).max() < 1e-9
+        assert abs(float(r.returns[0, e]) - float(clean.returns[0, e])) > 1e-3          # the noise is really applied
+
+
+def test_validate_agent_on_user_references_matches_the_reference_loop():
+    """base/evaluate.py:59-150 restated on the oracle env vs serl_b200.evaluation.validate_agent (one traced launch)."""
+    from serl_b200 import evaluation, rollout, signals
+    from serl_b200.envs import config
+    from serl_b200.core.utils import calc_nMAE, calc_smoothness
+    g = ACT['serl10_elite_h72_tanh']
+    t_max = 80
+    times = np.linspace(0., t_max, 6)
+    refs = [(signals.SmoothedStepSequence(times, [0, 12, 3, -4, -8, 2], smooth_width=t_max // 10),
+             signals.SmoothedStepSequence(times, [2, -2, 2, 10, 2, -6], smooth_width=t_max // 10)),
+            (signals.SmoothedStepSequence(times, [0, -6, 6, 9, -3, 0], smooth_width=t_max // 10),
+             signals.SmoothedStepSequence(times, [0, 5, -5, 0, 10, 0], smooth_width=t_max // 10))]
+    env = config.select_env('PHlab_attitude_ice')
+    env.set_eval_mode(t_max)
+    data, stats = evaluation.validate_agent(g, rollout.actor_shape(72), env, refs, num_trails=1)
+    # the reference's loop on the oracle env
+    nm, sm = [], []
+    for th, ph in refs:
+        oenv = phlab.CitationEnv('ice', 'auto', t_max=t_max)
+        oenv.smooth_w = float(th.smooth_width)
+        obs = oenv.reset(np.stack([th.levels, ph.levels]), np.stack([th.starts, ph.starts]))
+        done, errs, us = False, [], []
+        while not done:
+            x_ctrl = oenv.x[[7, 6, 5]].copy()
+            us.append(oenv.last_u.copy())
+            ref_value = np.deg2rad(oenv.ref_deg())
+            obs, rew, done, _ = oenv.step(KOActor(g).select_action(obs))
+            errs.append(ref_value - x_ctrl)
+        nm.append(calc_nMAE(np.asarray(errs)))
+        sm.append(calc_smoothness(np.asarray(us)))
+    assert data.shape[1] == 3 + 3 + 12 + 1 and data.shape[0] == len(errs)
+    assert abs(stats.nmae - np.average(nm)) <= 1e-5 * abs(np.average(nm)), (stats, nm)
+    assert abs(stats.sm - np.average(sm)) <= 1e-5 * abs(np.average(sm)), (stats, sm)
+
+
+def test_calc_nmae_literal():
+    from serl_b200.core.utils import calc_nMAE
+    e = np.random.RandomState(1).randn(500, 3) * 0.02
+    mae = np.mean(np.absolute(e), axis=0)
+    rng = np.array([np.deg2rad(20), np.deg2rad(20), max(np.abs(np.average(e[:, -1])), 3.14159 / 180)])
+    assert calc_nMAE(e) == pytest.approx(np.mean(mae / rng) * 100, rel=1e-14)
+
+
+def test_noise_mode_and_time_triggered_modes_are_named():
+    from serl_b200.envs import config
+    assert config.select_env('PHlab_attitude_noise').sensor_noise
+    with pytest.raises(ValueError):
+        config.select_env('PHlab_attitude_gust')
