@@ -1,10 +1,16 @@
 """Mirror of base/core/mod_neuro_evo.py SSNE (:14-543) on top of the device kernels K2-K5 (serl_b200/evo.py).
 
 Same constructor and `epoch(pop, fitness_evals, bcs_evals=None) -> int` contract; `pop` must be the engine's
-PopulationList (its genomes are mutated in place on the GPU).  Only the classic operators are implemented; asking for
-proximal / safe mutation or distillation crossover raises, as the reference does for unknown operators (:38, :507).
+PopulationList (its genomes are mutated in place on the GPU).  Mutation operators: classic Gaussian point mutation
+('normal' / 'inplace', K5) and the Jacobian-scaled 'proximal' / 'safe' mutations (:183-327) batched over the population
+(serl_b200/evo_prox.py, exact against the reference module).  Distillation crossover (:131-181, per-child behaviour-cloning
+training loops) is not implemented and raises, as the reference does for unknown operators (:38, :507).
 """
-from .. import evo
+import random
+
+import torch
+
+from .. import evo, evo_prox
 
 
 class SSNE:
@@ -20,8 +26,8 @@ class SSNE:
         if self.args.mut_type in ('normal', 'inplace'):
             self.mutate = None       # classic mutation runs inside epoch() (K5)
         elif self.args.mut_type in ('proximal', 'safe'):
-            raise NotImplementedError("mut_type '%s' needs per-actor replay buffers + autograd (SURVEY.md 8(f) N3); "
-                                      "use -mut_type normal" % self.args.mut_type)
+            self.mutate = self.args.mut_type      # batched over the population inside epoch() (serl_b200/evo_prox.py)
+            self._mut_gen = None
         else:
             raise ValueError('Mutation type is unknown!')
         if getattr(self.args, 'distil_crossover', False):
@@ -44,9 +50,11 @@ class SSNE:
         genomes = getattr(pop, 'genomes', None)
         if genomes is None:
             raise TypeError('SSNE.epoch needs the engine population (serl_b200.population.PopulationList)')
+        classic = self.mutate is None
         elite, plan = evo.epoch_flat(genomes, fitness_evals, pop.shape_tuple,
                                      elite_fraction=self.args.elite_fraction, mutation_prob=self.args.mutation_prob,
-                                     mutation_mag=self.args.mutation_mag, selection=self._selection_bookkeeping)
+                                     mutation_mag=self.args.mutation_mag, selection=self._selection_bookkeeping,
+                                     classic_mutation=classic)
         self.last_plan = plan
         # clone() also copies the per-agent replay buffers (:377-382); host-side bookkeeping, in the reference's order
         for wave in plan.clone_waves:
@@ -56,6 +64,16 @@ class SSNE:
             for g1, g2, s1, s2, _, _ in desc:
                 _copy_buffers(pop[int(s1)], pop[int(g1)])
                 _copy_buffers(pop[int(s2)], pop[int(g2)])
+        if not classic:
+            # :537-539: every non-elite rank mutates with probability mutation_prob (one random.random() each, in rank order)
+            chosen = [i for i in plan.mut_candidates if random.random() < self.args.mutation_prob]
+            if chosen:
+                if self._mut_gen is None:
+                    self._mut_gen = torch.Generator(device=genomes.device)
+                    self._mut_gen.manual_seed(int(getattr(self.args, 'seed', 7)) + 1)
+                states = evo_prox.mutation_states(pop, chosen, int(self.args.mutation_batch_size), safe=self.mutate == 'safe')
+                evo_prox.proximal_mutate_batched(genomes, chosen, states, pop.shape_tuple, self.args.activation_actor,
+                                                 float(self.args.mutation_mag), generator=self._mut_gen)
         self.current_gen += 1
         return elite
 

@@ -46,7 +46,7 @@ def _waves(items, reads, writes):
 
 class EvoPlan:
     __slots__ = ('clone_waves', 'cross_waves', 'mut_seg', 'mut_off', 'mut_kind', 'mut_z', 'elite', 'new_elitists',
-                 'offsprings', 'unselects', 'n_cross_ops', 'timing', 'elitist_index')
+                 'offsprings', 'unselects', 'n_cross_ops', 'timing', 'elitist_index', 'mut_candidates')
 
 
 def plan_epoch(index_rank, offsprings_raw, table, population_size, num_elitists, mutation_prob, selection=None, native=False):
@@ -86,7 +86,7 @@ def plan_epoch(index_rank, offsprings_raw, table, population_size, num_elitists,
     plan.elitist_index = [int(i) for i in elitist_index]       # the ranked elites; new_elitists[k] is the protected clone of [k]
     plan.timing = None
     if native:
-        return _plan_tail_native(plan, table, index_rank[num_elitists:], mutation_prob)
+        return _plan_tail_native(plan, table, index_rank[num_elitists:] if mutation_prob >= 0 else [], max(mutation_prob, 0.0))
     pairs, ops = [], []
     rnd, rrange, rint = random.random, random.randrange, random.randint
     for i, j in zip(unselects[0::2], unselects[1::2]):
@@ -110,7 +110,7 @@ def plan_epoch(index_rank, offsprings_raw, table, population_size, num_elitists,
     # :537-539 mutation of every non-elite rank (mutate_inplace :329-369)
     seg, m_off, m_kind, m_z = [], [], [], []
     gauss = random.gauss
-    for i in index_rank[num_elitists:]:
+    for i in (index_rank[num_elitists:] if mutation_prob >= 0 else []):
         if rnd() < mutation_prob:
             ssne_probabilities = np.random.uniform(0, 1, len(table)) * 2
             for k, (off, rows, cols) in enumerate(table):
@@ -223,7 +223,8 @@ def apply_plan(weights, plan, mutation_mag):
     torch.cuda.current_stream(dev).synchronize()      # op buffers must outlive the kernels
 
 
-def epoch_flat(weights, fitness, shape, elite_fraction=0.2, mutation_prob=0.9, mutation_mag=0.0247682869654, selection=None):
+def epoch_flat(weights, fitness, shape, elite_fraction=0.2, mutation_prob=0.9, mutation_mag=0.0247682869654, selection=None,
+               classic_mutation=True):
     """One generation on device genomes. weights [pop,P] fp32 cuda (modified in place); fitness: cuda f64 tensor or array-like.
     shape = (state_dim, action_dim, hidden, num_layers). Returns (new elite index, plan)."""
     if not weights.is_cuda:
@@ -240,7 +241,10 @@ def epoch_flat(weights, fitness, shape, elite_fraction=0.2, mutation_prob=0.9, m
     t0 = time.perf_counter()
     index_rank, offs_raw = select_device(fitness, num_elitists)
     t1 = time.perf_counter()
-    plan = plan_epoch(index_rank, offs_raw, table, pop, num_elitists, mutation_prob, selection, native=True)
+    # classic_mutation=False (proximal / safe mutation, core/mod_neuro_evo.py): the planner emits no Gaussian point
+    # mutations and consumes no draws for them; the caller draws the per-actor decisions itself, in the reference's order
+    plan = plan_epoch(index_rank, offs_raw, table, pop, num_elitists, mutation_prob if classic_mutation else -1.0, selection, native=True)
+    plan.mut_candidates = [int(i) for i in index_rank[num_elitists:]]
     t2 = time.perf_counter()
     apply_plan(weights, plan, mutation_mag)
     t3 = time.perf_counter()

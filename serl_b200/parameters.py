@@ -60,12 +60,7 @@ class Parameters:
             self.mutation_mag = 0.0247682869654
             self.mutation_batch_size = self.batch_size
             self.mut_type = g('mut_type', 'normal')
-            if self.mut_type in ('proximal', 'safe'):
-                import warnings
-                warnings.warn("mut_type '%s' (base/train.py's CLI default is 'proximal') is not implemented by the B200 engine; "
-                              "running the classic Gaussian mutation (mut_type 'normal', mod_neuro_evo.py:329-369) instead"
-                              % self.mut_type, RuntimeWarning, stacklevel=2)
-                self.mut_type = 'normal'
+            # 'proximal' (base/train.py's CLI default) and 'safe' are implemented batched on the device (serl_b200/evo_prox.py)
             self.distil_crossover = False
             self.distil_type = g('distil_type', 'distance')
             self.crossover_prob = 0.0

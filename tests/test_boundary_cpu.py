@@ -48,8 +48,11 @@ def test_ssne_rejects_out_of_scope_operators():
     from serl_b200.core.mod_neuro_evo import SSNE
     args = make_args()
     args.mut_type = 'proximal'
+    assert SSNE(args, None, None).mutate == 'proximal'        # batched on the device (serl_b200/evo_prox.py)
+    args.distil_crossover = True
     with pytest.raises(NotImplementedError):
         SSNE(args, None, None)
+    args.distil_crossover = False
     args.mut_type = 'bogus'
     with pytest.raises(ValueError):
         SSNE(args, None, None)

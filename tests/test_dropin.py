@@ -57,15 +57,25 @@ def test_copy_free_launcher_runs_the_train_py_call_sequence(tmp_path):
     check_checkpoints(tmp_path / 'tmp')
 
 
-def test_proximal_default_is_downgraded_with_a_warning():
-    """base/train.py's CLI default is -mut_type proximal: the engine says so instead of silently running something else."""
+@pytest.mark.gpu
+def test_launcher_with_the_reference_default_proximal_mutation(tmp_path):
+    """base/train.py:32 defaults to -mut_type proximal: the Jacobian-scaled mutation runs batched on the device, fed by the
+    per-actor device replay buffers the rollout kernel fills."""
+    args = ['-frames', '9000', '-pop_size', '6', '-mut_type', 'proximal', '-test_ea']
+    p = subprocess.run([sys.executable, os.path.join(ROOT, 'examples', 'train.py')] + args, cwd=tmp_path, capture_output=True, text=True,
+                       timeout=1800)
+    assert p.returncode == 0, p.stderr[-3000:]
+    check_checkpoints(tmp_path / 'tmp')
+
+
+def test_proximal_default_of_train_py_is_kept():
+    """base/train.py's CLI default is -mut_type proximal: implemented (serl_b200/evo_prox.py), so Parameters keeps it."""
     import types
     from serl_b200.parameters import Parameters
     cwd = os.getcwd()
     os.chdir('/tmp')
     try:
-        with pytest.warns(RuntimeWarning, match='proximal'):
-            a = Parameters(types.SimpleNamespace(mut_type='proximal', pop_size=4))
+        a = Parameters(types.SimpleNamespace(mut_type='proximal', pop_size=4))
     finally:
         os.chdir(cwd)
-    assert a.mut_type == 'normal'
+    assert a.mut_type == 'proximal'
