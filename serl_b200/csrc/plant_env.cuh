@@ -305,7 +305,7 @@ __device__ __forceinline__ void apply_fault(int fault, const double* u, double* 
 }
 
 // bind the env's constants (plant variant row, fault shim, reference signals, trim pitch); no dynamics
-__device__ __forceinline__ void env_bind(Env& e, const RolloutArgs& a, int env, const real* pv_base)
+__device__ __forceinline__ void env_bind(Env& e, const RolloutArgs& a, int env, const real* pv_base, size_t traj = 0)
 {
     const int mode = a.env_mode[env];
     const int variant = mode & 0xff;
@@ -313,7 +313,10 @@ __device__ __forceinline__ void env_bind(Env& e, const RolloutArgs& a, int env, 
     e.fault = (mode >> 8) & 0xff;
     e.ref_lv = a.ref_levels + (size_t)env * 2 * SERL_REF_BLOCKS;
     e.ref_st = a.ref_starts + (size_t)env * 2 * SERL_REF_BLOCKS;
-    e.theta_trim = plant_ic(variant)[7] * RAD2DEG;
+    // theta_trim = rad2deg(theta) of reset()'s step output (phlabenv.py:317) — with the sensor-noise shim that output is noisy
+    double th0 = plant_ic(variant)[7];
+    if (a.sensor_noise) th0 += 4.0 * 1e-3 + 3.2 * 1e-5 * (double)a.sensor_noise[traj * (size_t)(a.horizon + 1) * 7 + 6];
+    e.theta_trim = th0 * RAD2DEG;
 }
 
 // sensor-noise shim (envs/noise/citation.py:72-82, same model in envs/gust): every native step() output gets

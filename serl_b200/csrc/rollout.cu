@@ -375,7 +375,7 @@ rollout_kernel_persist(RolloutArgs ar)
             __threadfence();
         }
         if (valid) {
-            env_bind(e, ar, env, pv_base);
+            env_bind(e, ar, env, pv_base, (size_t)actor * ar.n_envs + env);
             if (from_h) {
                 const long long hx = (slot - 1) * slot_threads + wslot * 32 + lane;
 #pragma unroll
@@ -445,7 +445,7 @@ rollout_kernel_simple(RolloutArgs ar)
     Env e;
     e.tab = plant_tables_blob;
     float obs[7], a[3];
-    env_bind(e, ar, env, &plant_pv[0][0]);
+    env_bind(e, ar, env, &plant_pv[0][0], (size_t)actor * ar.n_envs + env);
     env_reset(e, ar, env, obs, (size_t)actor * ar.n_envs + env);
     const size_t traj = (size_t)actor * ar.n_envs + env;
     const bool replay = ar.replay != nullptr && env == ar.replay_env;
@@ -620,13 +620,157 @@ smoothness_kernel(const float* __restrict__ actions, const int* __restrict__ ste
     }
 }
 
+// ---- K6 (fast path): the same metric through a Bluestein (chirp-z) FFT --------------------------------------------
+// N (the episode length) is arbitrary (2001 = 3*23*29 for a full episode, anything for an early termination), so the
+// length-N DFT is written as a circular convolution of size FM = 4096 >= 2N-1 with the chirp b[m] = exp(i pi m^2 / N):
+//   Y[k] = conj(b[k]) * sum_n (y[n] conj(b[n])) b[k-n]
+// = three radix-2 FFTs of size 4096 in shared memory per transform (forward DIF: natural -> bit-reversed order; the
+// pointwise product with the chirp spectrum in bit-reversed order; inverse DIT: bit-reversed -> natural), O(N log N)
+// instead of the O(N^2) of the direct form.  Two real channels share one complex transform (their spectra are separated by
+// conjugate symmetry), the channel means are removed first (bin 0 is not part of the metric), phases are reduced exactly
+// in integer arithmetic (m^2 mod 2N).  One CTA per trajectory.
+#define FM 4096
+#define FLOG 12
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ float2 chirp(int m, int N)      // exp(+i pi m^2 / N)
+{
+    const int r = (int)(((long long)m * m) % (2 * N));
+    float s, c;
+    sincospif((float)r / (float)N, &s, &c);
+    return make_float2(c, s);
+}
+// forward FFT, decimation in frequency: natural order in, bit-reversed order out; tw[j] = exp(-2 pi i j / FM)
+__device__ void fft_dif(float2* z, const float2* tw, int tid, int nthr)
+{
+    for (int lh = FLOG - 1; lh >= 0; --lh) {
+        const int half = 1 << lh;
+        for (int j = tid; j < FM / 2; j += nthr) {
+            const int pos = j & (half - 1), i0 = ((j >> lh) << (lh + 1)) + pos, i1 = i0 + half;
+            const float2 a = z[i0], b = z[i1];
+            z[i0] = make_float2(a.x + b.x, a.y + b.y);
+            z[i1] = cmul(make_float2(a.x - b.x, a.y - b.y), tw[pos << (FLOG - 1 - lh)]);
+        }
+        __syncthreads();
+    }
+}
+// inverse FFT (unnormalised), decimation in time: bit-reversed order in, natural order out
+__device__ void ifft_dit(float2* z, const float2* tw, int tid, int nthr)
+{
+    for (int lh = 0; lh < FLOG; ++lh) {
+        const int half = 1 << lh;
+        for (int j = tid; j < FM / 2; j += nthr) {
+            const int pos = j & (half - 1), i0 = ((j >> lh) << (lh + 1)) + pos, i1 = i0 + half;
+            const float2 t = tw[pos << (FLOG - 1 - lh)];
+            const float2 a = z[i0], b = cmul(z[i1], make_float2(t.x, -t.y));
+            z[i0] = make_float2(a.x + b.x, a.y + b.y);
+            z[i1] = make_float2(a.x - b.x, a.y - b.y);
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256)
+smoothness_fft_kernel(const float* __restrict__ actions, const int* __restrict__ steps, int horizon, double dt, double* __restrict__ out)
+{
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    float2* z = reinterpret_cast<float2*>(sm_raw);            // [FM] work buffer
+    float2* hf = z + FM;                                      // [FM] spectrum of the chirp filter (bit-reversed order)
+    float2* tw = hf + FM;                                     // [FM/2] twiddles
+    __shared__ double red[256];
+    __shared__ float mean_s[3];
+    const int traj = blockIdx.x, tid = threadIdx.x;
+    const int N = steps[traj];
+    const int Mb = N / 2 - 1;
+    if (Mb <= 0) { if (tid == 0) out[traj] = -0.0; return; }
+    const float* a = actions + (size_t)traj * horizon * 3;
+    for (int j = tid; j < FM / 2; j += 256) {
+        float s, c;
+        sincospif(-2.0f * (float)j / (float)FM, &s, &c);
+        tw[j] = make_float2(c, s);
+    }
+    // channel means (bin 0 is excluded from the metric; removing it keeps the float32 transform accurate)
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    for (int n = tid; n < N; n += 256) { s0 += a[3 * n]; s1 += a[3 * n + 1]; s2 += a[3 * n + 2]; }
+    for (int c = 0; c < 3; ++c) {
+        red[tid] = c == 0 ? s0 : (c == 1 ? s1 : s2);
+        __syncthreads();
+        for (int s = 128; s > 0; s >>= 1) { if (tid < s) red[tid] += red[tid + s]; __syncthreads(); }
+        if (tid == 0) mean_s[c] = (float)(red[0] / (double)N);
+        __syncthreads();
+    }
+    // chirp filter h[m] = b[|m|] for |m| < N (circular), its forward transform stays in hf
+    for (int m = tid; m < FM; m += 256) {
+        const int d = m < N ? m : (FM - m < N ? FM - m : -1);
+        hf[m] = d >= 0 ? chirp(d, N) : make_float2(0.f, 0.f);
+    }
+    __syncthreads();
+    fft_dif(hf, tw, tid, 256);
+    const double fstep = Mb > 1 ? (1.0 / (2.0 * dt) - dt) / (double)(Mb - 1) : 0.0;
+    const float inv_m = 1.0f / (float)FM;
+    double acc = 0.0;
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int n = tid; n < FM; n += 256) {
+            float2 v = make_float2(0.f, 0.f);
+            if (n < N) {
+                const float re = pass == 0 ? a[3 * n] - mean_s[0] : a[3 * n + 2] - mean_s[2];
+                const float im = pass == 0 ? a[3 * n + 1] - mean_s[1] : 0.f;
+                const float2 b = chirp(n, N);
+                v = cmul(make_float2(re, im), make_float2(b.x, -b.y));
+            }
+            z[n] = v;
+        }
+        __syncthreads();
+        fft_dif(z, tw, tid, 256);
+        for (int m = tid; m < FM; m += 256) z[m] = cmul(z[m], hf[m]);
+        __syncthreads();
+        ifft_dit(z, tw, tid, 256);
+        for (int k = 1 + tid; k <= Mb; k += 256) {
+            const double f = dt + (double)(k - 1) * fstep;
+            if (pass == 0) {
+                // T[k] = conj(b[k]) c[k] = Y0[k] + i Y1[k];  Y0 = (T[k] + conj(T[N-k])) / 2,  Y1 = (T[k] - conj(T[N-k])) / (2i)
+                const float2 bk = chirp(k, N), bn = chirp(N - k, N);
+                float2 tk = cmul(z[k], make_float2(bk.x, -bk.y)), tn = cmul(z[N - k], make_float2(bn.x, -bn.y));
+                tk.x *= inv_m; tk.y *= inv_m; tn.x *= inv_m; tn.y *= inv_m;
+                const float y0r = 0.5f * (tk.x + tn.x), y0i = 0.5f * (tk.y - tn.y);
+                const float y1r = 0.5f * (tk.y + tn.y), y1i = 0.5f * (tn.x - tk.x);
+                acc += f * ((double)y0r * y0r + (double)y0i * y0i + (double)y1r * y1r + (double)y1i * y1i);
+            } else {
+                const float cr = z[k].x * inv_m, ci = z[k].y * inv_m;
+                acc += f * ((double)cr * cr + (double)ci * ci);
+            }
+        }
+        __syncthreads();
+    }
+    red[tid] = acc;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) { if (tid < s) red[tid] += red[tid + s]; __syncthreads(); }
+    if (tid == 0) {
+        const double S = red[0] * dt * 2.0 / (double)N;
+        out[traj] = -(sqrt(S) * 100.0 * (80.0 / ((double)N * dt)));
+    }
+}
+
 extern "C" int serl_smoothness(const float* d_actions, const int32_t* d_steps, int32_t n_traj, int32_t horizon, double dt,
                                double* d_out, void* stream)
 {
     if (!d_actions || !d_steps || !d_out || n_traj <= 0 || horizon <= 0) return serl_fail(SERL_ERR_ARG, "serl_smoothness: bad argument");
+    static int force_direct = -1;
+    if (force_direct < 0) { const char* v = getenv("SERL_SMOOTHNESS_IMPL"); force_direct = (v && strcmp(v, "direct") == 0) ? 1 : 0; }
+    cudaError_t e;
+    if (!force_direct && 2 * horizon - 1 <= FM) {
+        // episodes of up to 2048 steps (training: 2001): Bluestein FFT, O(N log N)
+        const size_t smem = (size_t)(2 * FM + FM / 2) * sizeof(float2);
+        e = cudaFuncSetAttribute(smoothness_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return serl_fail_cuda(e, "cudaFuncSetAttribute(smoothness_fft)");
+        smoothness_fft_kernel<<<n_traj, 256, smem, (cudaStream_t)stream>>>(d_actions, d_steps, horizon, dt, d_out);
+        serl_count_launch();
+        e = cudaGetLastError();
+        return e == cudaSuccess ? SERL_OK : serl_fail_cuda(e, "smoothness_fft_kernel");
+    }
+    // longer episodes (80 s evaluation mode: 8001 steps): direct DFT
     const size_t smem = (size_t)horizon * (8 + 12);
     if (smem > 200 * 1024) return serl_fail(SERL_ERR_UNSUPPORTED, "serl_smoothness: horizon too long for the shared-memory DFT");
-    cudaError_t e = cudaFuncSetAttribute(smoothness_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(smoothness_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return serl_fail_cuda(e, "cudaFuncSetAttribute(smoothness)");
     smoothness_kernel<<<n_traj, 256, smem, (cudaStream_t)stream>>>(d_actions, d_steps, horizon, dt, d_out);
     serl_count_launch();

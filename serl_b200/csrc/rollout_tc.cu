@@ -354,7 +354,7 @@ rollout_kernel_tc(TcArgs ar)
         e.tab = plant_tables_blob;                       // plant tables through L1 (shared memory holds the weight ring)
         float obs[7], a[3];
         if (valid) {
-            env_bind(e, r, env, &plant_pv[0][0]);
+            env_bind(e, r, env, &plant_pv[0][0], (size_t)actor * r.n_envs + env);
             env_reset(e, r, env, obs, (size_t)actor * r.n_envs + env);
         } else {
             e.done = true; e.k = 0; e.ret = 0.0; e.t = 0.0; e.fault = 0; e.pv = &plant_pv[0][0]; e.theta_trim = 0.0;
