@@ -25,7 +25,9 @@
 #include "plant_env.cuh"
 
 #define TC_THREADS 128
+#ifndef TC_STAGES
 #define TC_STAGES 3
+#endif
 #define TC_KSLAB 8                 // K values per pipeline stage = one tcgen05.mma K step for TF32
 
 struct TcArgs {
