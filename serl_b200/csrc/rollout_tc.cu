@@ -4,7 +4,10 @@
 //   actor  Linear(7,w1) -> act -> Linear(w1,w2) -> LayerNorm(w2) -> act -> Linear(w2,3) -> tanh
 //          (the two-hidden-layer generalisation of base/core/genetic_agent.py:78-101; LayerNorm base/core/mod_utils.py:47-50)
 //
-// A CTA = 128 threads = 128 envs of one actor (thread = env = row of the layer GEMM = TMEM lane), two CTAs per SM.  Per step:
+// One CTA per SM = 256 threads = two GROUPS of 128 threads; a group = 128 envs of one actor (thread = env = row of the layer
+// GEMM = TMEM lane).  The two groups run independent task loops, share the plant tables in shared memory, the weight ring,
+// the TMEM accumulator and the tensor core, and take turns on them (a shared-memory lock): while one group streams its W1
+// slabs through the tensor core the other integrates its plant step.  Per step of a group:
 //   layer 1   on CUDA cores, 8 neurons at a time: every thread computes its env's activations and writes them, split
 //             into TF32 hi + lo parts, as one K-slab of the A operand in shared memory (UMMA canonical K-major layout,
 //             no swizzle);
@@ -16,9 +19,9 @@
 //   epilogue  tcgen05.ld brings the thread's accumulator row out of TMEM 16 columns at a time: bias, LayerNorm (the whole
 //             row lives in one thread: no shuffles), activation, and the 3-row output layer folded into the same pass;
 //   plant     CitationEnv.step + the ode5 plant step on CUDA cores (plant_env.cuh), exactly as in K1.
-// The two CTAs of an SM alternate naturally: one streams weights through the tensor core while the other integrates the
-// plant.  w2 > 256 needs all 512 TMEM columns, so such a CTA allocates TMEM per step and releases it after the
-// epilogue (tcgen05.alloc blocks while the sibling CTA holds the columns).
+// (Round-2 history: the first version ran two 128-thread CTAs per SM with the plant tables read through L1; at [400,300]
+// the two weight rings left ~50 KB of L1 and the plant's table / local-memory traffic thrashed it — 26 % long-scoreboard
+// stalls, 1.1e8 env-steps/s.  Sharing one ring, one accumulator and shared-memory tables between two groups fixed that.)
 //
 // Numerics: tensor-core accumulation order is not reproducible on a CPU, so this path is checked against the torch fp32
 // oracle with a tolerance (tests/test_wide_actor_gpu.py), not bit for bit like K1.
@@ -28,11 +31,15 @@
 #ifndef TC_STAGES
 #define TC_STAGES 3
 #endif
-#define TC_KSLAB 8                 // K values per pipeline stage = one tcgen05.mma K step for TF32
+#ifndef TC_KSLAB
+#define TC_KSLAB 8                 // K values per pipeline stage (a multiple of 8 = the tcgen05.mma K step for TF32)
+#endif
+#define TC_CH (TC_KSLAB / 4)        // 16-byte K chunks (4 TF32 values) per stage
 
 struct TcArgs {
     RolloutArgs r;                 // env / output part (weights, wt, P4, apc ... unused)
-    int w1, w2, n2pad;             // layer widths; w2 padded to a multiple of 16
+    int w1, w2, n2pad;             // layer widths (w1 already padded to a multiple of TC_KSLAB with zero neurons); w2 padded to 16
+    int w1_real;
     int tmem_cols;                 // TMEM columns to allocate (power of two >= 32)
     int small_floats;              // per-actor small parameter block (floats, multiple of 4)
     int stage_floats;              // per-stage W1 slab: hi[2][n2pad][4] + lo[2][n2pad][4]
@@ -52,13 +59,14 @@ __device__ __forceinline__ float rn_tf32(float x)       // round to nearest TF32
 __host__ __device__ inline int tc_small_floats(int w1, int n2pad) { return w1 * 8 + 6 * n2pad + 4; }
 
 // K0-TC: genome (parameters() order: W0[w1,7] b0[w1] W1[w2,w1] b1 gamma beta Wo[3,w2] bo[3]) -> small block + W1 slabs
-__global__ void tc_layout_kernel(const float* __restrict__ w, int pop, int P, int w1, int w2, int n2pad, int small_floats,
+__global__ void tc_layout_kernel(const float* __restrict__ w, int pop, int P, int w1, int w1r, int w2, int n2pad, int small_floats,
                                  int stage_floats, float* __restrict__ small, float* __restrict__ tiles)
 {
     const int n_stages = w1 / TC_KSLAB;
     const long long per = (long long)small_floats + (long long)n_stages * stage_floats;
     const long long total = (long long)pop * per;
-    const int oW1 = 8 * w1, ob1 = oW1 + w2 * w1, og = ob1 + w2, obe = og + w2, oWo = obe + w2, obo = oWo + 3 * w2;
+    // genome offsets use the REAL layer-1 width w1r; rows / columns w1r..w1 of the kernel layout are zero neurons
+    const int oW1 = 8 * w1r, ob1 = oW1 + w2 * w1r, og = ob1 + w2, obe = og + w2, oWo = obe + w2, obo = oWo + 3 * w2;
     for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
         const int a = (int)(g / per);
         long long i = g - (long long)a * per;
@@ -66,7 +74,7 @@ __global__ void tc_layout_kernel(const float* __restrict__ w, int pop, int P, in
         if (i < small_floats) {
             float v = 0.f;
             int r = (int)i;
-            if (r < w1 * 8) { const int k = r >> 3, c = r & 7; v = c < 7 ? ga[k * 7 + c] : ga[7 * w1 + k]; }
+            if (r < w1 * 8) { const int k = r >> 3, c = r & 7; v = k >= w1r ? 0.f : (c < 7 ? ga[k * 7 + c] : ga[7 * w1r + k]); }
             else {
                 r -= w1 * 8;
                 if (r < n2pad) v = r < w2 ? ga[ob1 + r] : 0.f;
@@ -80,12 +88,12 @@ __global__ void tc_layout_kernel(const float* __restrict__ w, int pop, int P, in
             i -= small_floats;
             const int s = (int)(i / stage_floats);
             int r = (int)(i - (long long)s * stage_floats);
-            const int half = 2 * n2pad * 4;
+            const int half = TC_CH * n2pad * 4;
             const int part = r / half;
             r -= part * half;
             const int j = r / (n2pad * 4), n = (r >> 2) % n2pad, kk = r & 3;
             const int k = s * TC_KSLAB + j * 4 + kk;
-            const float v = n < w2 ? ga[oW1 + n * w1 + k] : 0.f;
+            const float v = (n < w2 && k < w1r) ? ga[oW1 + n * w1r + k] : 0.f;
             const float hi = rn_tf32(v);
             tiles[(size_t)a * n_stages * stage_floats + (size_t)s * stage_floats + (i - (long long)s * stage_floats)] =
                 part == 0 ? hi : rn_tf32(v - hi);
@@ -139,31 +147,56 @@ struct TcCtx {
     uint64_t* free_s;              // [TC_STAGES] MMAs of the slot retired
     uint64_t* acc_bar;             // accumulator complete
     uint32_t* tmem_slot;           // smem word tcgen05.alloc writes
-    uint32_t g;                    // stages issued so far (uniform over the CTA)
-    uint32_t steps;                // accumulators completed so far
-    uint32_t tmem;                 // current TMEM base address
-    bool tmem_per_step;
+    uint32_t g;                    // stages issued so far (valid while the group holds the lock)
+    uint32_t steps;                // accumulators completed so far (same)
+    uint32_t tmem;                 // TMEM base address
+    uint32_t* shared_state;        // smem: {lock, g, steps} shared by the two groups
+    int grp, gtid;                 // group of this thread (0/1), thread index inside the group
 };
+
+__device__ __forceinline__ void group_sync(int grp) { asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(TC_THREADS) : "memory"); }
+__device__ __forceinline__ bool group_any(int grp, bool pred)
+{
+    uint32_t r;
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %1, 0;\n\tbar.red.or.pred p, %2, %3, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(r) : "r"((uint32_t)pred), "r"(3 + grp), "r"(TC_THREADS) : "memory");
+    return r != 0;
+}
+// the tensor core, its accumulator and the A / W1 rings belong to one group at a time
+__device__ __forceinline__ void tc_acquire(TcCtx& c)
+{
+    if (c.gtid == 0) {
+        while (atomicCAS(&c.shared_state[0], 0u, 1u) != 0u) __nanosleep(100);
+        __threadfence_block();
+    }
+    group_sync(c.grp);
+    c.g = *reinterpret_cast<volatile uint32_t*>(&c.shared_state[1]);
+    c.steps = *reinterpret_cast<volatile uint32_t*>(&c.shared_state[2]);
+}
+__device__ __forceinline__ void tc_release(TcCtx& c)
+{
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    group_sync(c.grp);                       // every warp of the group has read its TMEM lanes
+    if (c.gtid == 0) {
+        c.shared_state[1] = c.g;
+        c.shared_state[2] = c.steps;
+        __threadfence_block();
+        atomicExch(&c.shared_state[0], 0u);
+    }
+}
 
 // one actor forward for the 128 envs of the CTA; every thread passes its own observation and receives its own action
 template <int ACT>
 __device__ __forceinline__ void tc_actor_forward(TcCtx& c, const TcArgs& ar, const float* tiles_actor, const float* obs, float* action)
 {
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = c.gtid, warp = tid >> 5;          // group-local: warp = TMEM lane quadrant of this thread
     const int w1 = ar.w1, w2 = ar.w2, n2pad = ar.n2pad;
     const int n_stages = w1 / TC_KSLAB;
     const uint32_t stage_bytes = (uint32_t)ar.stage_floats * 4u;
-    constexpr int A_STAGE_FLOATS = 2 * 2 * TC_THREADS * 4;                 // hi + lo, 2 chunks x 128 rows x 4 floats
+    constexpr int A_STAGE_FLOATS = 2 * TC_CH * TC_THREADS * 4;             // hi + lo, TC_CH chunks x 128 rows x 4 floats
     const float* W0p = c.small;
-    if (c.tmem_per_step) {
-        if (warp == 0) {
-            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(c.tmem_slot)), "r"(ar.tmem_cols) : "memory");
-        }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        c.tmem = *reinterpret_cast<volatile uint32_t*>(c.tmem_slot);
-    }
+    tc_acquire(c);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t g0 = c.g;
     // W1 slabs of the first stages of this step (their slots were released by the previous step's MMAs)
     if (tid == 0) {
@@ -182,9 +215,9 @@ __device__ __forceinline__ void tc_actor_forward(TcCtx& c, const TcArgs& ar, con
         if (g >= TC_STAGES) mbar_wait(&c.free_s[slot], ((g / TC_STAGES) + 1) & 1);
         // layer 1: this env's 8 activations of the slab, split into TF32 hi / lo, as A rows
         float* a_hi = c.a_ring + (size_t)slot * A_STAGE_FLOATS;
-        float* a_lo = a_hi + 2 * TC_THREADS * 4;
+        float* a_lo = a_hi + TC_CH * TC_THREADS * 4;
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
+        for (int j = 0; j < TC_CH; ++j) {
             float h[4];
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
@@ -203,24 +236,28 @@ __device__ __forceinline__ void tc_actor_forward(TcCtx& c, const TcArgs& ar, con
             *reinterpret_cast<float4*>(a_lo + ((size_t)j * TC_THREADS + tid) * 4) = lo;
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes of A -> tensor-core (async proxy) reads
-        __syncthreads();
+        group_sync(c.grp);
         if (tid == 0) {
             mbar_wait(&c.full_b[slot], (g / TC_STAGES) & 1);               // W1 slab landed
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t a_hi_addr = smem_u32(a_hi), a_lo_addr = smem_u32(a_lo);
             const uint32_t b_hi_addr = smem_u32(c.b_ring + (size_t)slot * ar.stage_floats);
-            const uint32_t b_lo_addr = b_hi_addr + 2u * (uint32_t)n2pad * 16u;
+            const uint32_t b_lo_addr = b_hi_addr + (uint32_t)TC_CH * (uint32_t)n2pad * 16u;
             const uint32_t lbo_a = TC_THREADS * 16, lbo_b = (uint32_t)n2pad * 16;
-            const uint64_t dah = umma_desc(a_hi_addr, lbo_a, 128), dal = umma_desc(a_lo_addr, lbo_a, 128);
-            const uint32_t acc0 = s > 0 ? 1u : 0u;
-            // N part 0 (columns 0 .. min(n2pad,256))
-            umma_tf32(c.tmem, dah, umma_desc(b_hi_addr, lbo_b, 128), idesc0, acc0);
-            umma_tf32(c.tmem, dah, umma_desc(b_lo_addr, lbo_b, 128), idesc0, 1u);
-            umma_tf32(c.tmem, dal, umma_desc(b_hi_addr, lbo_b, 128), idesc0, 1u);
-            if (n2pad > 256) {                                                 // N part 1 (columns 256 .. n2pad)
-                umma_tf32(c.tmem + 256, dah, umma_desc(b_hi_addr + 256 * 16, lbo_b, 128), idesc1, acc0);
-                umma_tf32(c.tmem + 256, dah, umma_desc(b_lo_addr + 256 * 16, lbo_b, 128), idesc1, 1u);
-                umma_tf32(c.tmem + 256, dal, umma_desc(b_hi_addr + 256 * 16, lbo_b, 128), idesc1, 1u);
+#pragma unroll
+            for (int ks = 0; ks < TC_KSLAB / 8; ++ks) {                         // one K step = two 16-byte chunks
+                const uint32_t ao = (uint32_t)(2 * ks) * lbo_a, bo2 = (uint32_t)(2 * ks) * lbo_b;
+                const uint64_t dah = umma_desc(a_hi_addr + ao, lbo_a, 128), dal = umma_desc(a_lo_addr + ao, lbo_a, 128);
+                const uint32_t acc0 = (s > 0 || ks > 0) ? 1u : 0u;
+                // N part 0 (columns 0 .. min(n2pad,256))
+                umma_tf32(c.tmem, dah, umma_desc(b_hi_addr + bo2, lbo_b, 128), idesc0, acc0);
+                umma_tf32(c.tmem, dah, umma_desc(b_lo_addr + bo2, lbo_b, 128), idesc0, 1u);
+                umma_tf32(c.tmem, dal, umma_desc(b_hi_addr + bo2, lbo_b, 128), idesc0, 1u);
+                if (n2pad > 256) {                                             // N part 1 (columns 256 .. n2pad)
+                    umma_tf32(c.tmem + 256, dah, umma_desc(b_hi_addr + bo2 + 256 * 16, lbo_b, 128), idesc1, acc0);
+                    umma_tf32(c.tmem + 256, dah, umma_desc(b_lo_addr + bo2 + 256 * 16, lbo_b, 128), idesc1, 1u);
+                    umma_tf32(c.tmem + 256, dal, umma_desc(b_hi_addr + bo2 + 256 * 16, lbo_b, 128), idesc1, 1u);
+                }
             }
             umma_commit(&c.free_s[slot]);                                      // slot reusable when these MMAs retire
             if (s == n_stages - 1) umma_commit(c.acc_bar);
@@ -247,6 +284,20 @@ __device__ __forceinline__ void tc_actor_forward(TcCtx& c, const TcArgs& ar, con
     const uint32_t trow = c.tmem + ((uint32_t)(warp * 32) << 16);
     const int n_chunks = n2pad / 16;
     float v[16];
+#ifdef TC_EPI2
+    // mean and variance in ONE pass over the accumulator row, shifted by its first element (no cancellation problem:
+    // |mean - x0| is of the order of the row's own spread)
+    float x0 = 0.f, s1 = 0.f, s2 = 0.f;
+    for (int ch = 0; ch < n_chunks; ++ch) {
+        tmem_ld16(trow + ch * 16, v);
+        if (ch == 0) x0 = __fadd_rn(v[0], b1[0]);
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            if (ch * 16 + i < w2) { const float d = __fadd_rn(__fadd_rn(v[i], b1[ch * 16 + i]), -x0); s1 = __fadd_rn(s1, d); s2 = __fmaf_rn(d, d, s2); }
+    }
+    const float mean = __fadd_rn(x0, __fdiv_rn(s1, (float)w2));
+    const float ss = fmaxf(__fmaf_rn(-s1, __fdiv_rn(s1, (float)w2), s2), 0.f);
+#else
     float sum = 0.f;
     for (int ch = 0; ch < n_chunks; ++ch) {
         tmem_ld16(trow + ch * 16, v);
@@ -262,6 +313,7 @@ __device__ __forceinline__ void tc_actor_forward(TcCtx& c, const TcArgs& ar, con
         for (int i = 0; i < 16; ++i)
             if (ch * 16 + i < w2) { const float d = __fadd_rn(__fadd_rn(v[i], b1[ch * 16 + i]), -mean); ss = __fmaf_rn(d, d, ss); }
     }
+#endif
     const float inv = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(__fdiv_rn(ss, (float)(w2 - 1))), 1e-6f));
     float o0 = 0.f, o1 = 0.f, o2 = 0.f;
     for (int ch = 0; ch < n_chunks; ++ch) {
@@ -281,71 +333,80 @@ __device__ __forceinline__ void tc_actor_forward(TcCtx& c, const TcArgs& ar, con
     action[0] = am_tanh1(__fadd_rn(o0, bo[0]));
     action[1] = am_tanh1(__fadd_rn(o1, bo[1]));
     action[2] = am_tanh1(__fadd_rn(o2, bo[2]));
-    // every warp has read its TMEM lanes: the accumulator may be overwritten (or released)
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (c.tmem_per_step && warp == 0) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(c.tmem), "r"(ar.tmem_cols) : "memory");
-    }
+    // every warp has read its TMEM lanes: hand the tensor core, the accumulator and the rings to the other group
+    tc_release(c);
 }
 
-__device__ __forceinline__ void tc_setup(TcCtx& c, const TcArgs& ar, unsigned char* smem_raw, uint64_t* bars, uint32_t* tmem_slot)
+constexpr int TC_TABN = PT_TOTAL + SERL_PLANT_COUNT * PLANT_NPV;      // plant tables + per-variant parameter rows
+constexpr int TC_TABN2 = (TC_TABN + 15) & ~15;                          // keeps the float regions 128-byte aligned
+
+__device__ __forceinline__ void tc_setup(TcCtx& c, const TcArgs& ar, unsigned char* smem_raw, uint64_t* bars, uint32_t* tmem_slot,
+                                         uint32_t* shared_state)
 {
-    constexpr int A_STAGE_FLOATS = 2 * 2 * TC_THREADS * 4;
-    float* f = reinterpret_cast<float*>(smem_raw);
-    c.small = f;
-    c.a_ring = f + ((ar.small_floats + 31) & ~31);
+    constexpr int A_STAGE_FLOATS = 2 * TC_CH * TC_THREADS * 4;
+    real* tab_s = reinterpret_cast<real*>(smem_raw);
+    for (int i = threadIdx.x; i < PT_TOTAL; i += blockDim.x) tab_s[i] = plant_tables_blob[i];
+    for (int i = threadIdx.x; i < SERL_PLANT_COUNT * PLANT_NPV; i += blockDim.x) tab_s[PT_TOTAL + i] = (&plant_pv[0][0])[i];
+    float* f = reinterpret_cast<float*>(tab_s + TC_TABN2);
+    const int small_pad = (ar.small_floats + 31) & ~31;
+    c.grp = threadIdx.x >> 7;
+    c.gtid = threadIdx.x & (TC_THREADS - 1);
+    c.small = f + (size_t)c.grp * small_pad;
+    c.a_ring = f + 2 * (size_t)small_pad;
     c.b_ring = c.a_ring + TC_STAGES * A_STAGE_FLOATS;
     c.full_b = bars; c.free_s = bars + TC_STAGES; c.acc_bar = bars + 2 * TC_STAGES;
     c.tmem_slot = tmem_slot;
+    c.shared_state = shared_state;
     c.g = 0; c.steps = 0; c.tmem = 0;
-    c.tmem_per_step = ar.tmem_cols > 256;
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2 * TC_STAGES + 1; ++i) mbar_init(&bars[i], 1);
+        shared_state[0] = shared_state[1] = shared_state[2] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (!c.tmem_per_step) {
-        if ((threadIdx.x >> 5) == 0) {
-            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(ar.tmem_cols) : "memory");
-            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-        }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        c.tmem = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+    if ((threadIdx.x >> 5) == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(ar.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    c.tmem = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 }
 
 __device__ __forceinline__ void tc_teardown(TcCtx& c, const TcArgs& ar)
 {
     __syncthreads();
-    if (!c.tmem_per_step && (threadIdx.x >> 5) == 0)
+    if ((threadIdx.x >> 5) == 0)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(c.tmem), "r"(ar.tmem_cols) : "memory");
 }
 
 __device__ __forceinline__ void tc_load_small(TcCtx& c, const TcArgs& ar, int actor)
 {
-    __syncthreads();                  // previous actor's parameters no longer read
+    group_sync(c.grp);                // the group's previous actor's parameters are no longer read
     float* dst = const_cast<float*>(c.small);
     const float4* src = reinterpret_cast<const float4*>(ar.small + (size_t)actor * ar.small_floats);
-    for (int i = threadIdx.x; i < ar.small_floats / 4; i += TC_THREADS) reinterpret_cast<float4*>(dst)[i] = src[i];
-    __syncthreads();
+    for (int i = c.gtid; i < ar.small_floats / 4; i += TC_THREADS) reinterpret_cast<float4*>(dst)[i] = src[i];
+    group_sync(c.grp);
 }
 
 template <int ACT>
-__global__ void __launch_bounds__(TC_THREADS, 2)
+__global__ void __launch_bounds__(2 * TC_THREADS, 1)
 rollout_kernel_tc(TcArgs ar)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bars[2 * TC_STAGES + 1];
     __shared__ uint32_t tmem_slot;
+    __shared__ uint32_t shared_state[4];
     TcCtx c;
-    tc_setup(c, ar, smem_raw, bars, &tmem_slot);
+    tc_setup(c, ar, smem_raw, bars, &tmem_slot, shared_state);
     const RolloutArgs& r = ar.r;
-    const int tid = threadIdx.x;
+    const real* tab = reinterpret_cast<const real*>(smem_raw);
+    const real* pv_base = tab + PT_TOTAL;
+    const int tid = c.gtid;
     const int n_stages = ar.w1 / TC_KSLAB;
-    for (long long task = blockIdx.x; task < ar.n_tasks; task += gridDim.x) {
+    // the two groups of a CTA run independent task loops
+    for (long long task = (long long)blockIdx.x * 2 + c.grp; task < ar.n_tasks; task += 2LL * gridDim.x) {
         const int actor = (int)(task / ar.n_chunks), chunk = (int)(task - (long long)actor * ar.n_chunks);
         tc_load_small(c, ar, actor);
         const float* tiles_actor = ar.tiles + (size_t)actor * n_stages * ar.stage_floats;
@@ -353,13 +414,13 @@ rollout_kernel_tc(TcArgs ar)
         const bool valid = eslot < r.n_envs;
         const int env = valid ? (r.env_order ? r.env_order[eslot] : eslot) : 0;
         Env e;
-        e.tab = plant_tables_blob;                       // plant tables through L1 (shared memory holds the weight ring)
+        e.tab = tab;
         float obs[7], a[3];
         if (valid) {
-            env_bind(e, r, env, &plant_pv[0][0], (size_t)actor * r.n_envs + env);
+            env_bind(e, r, env, pv_base, (size_t)actor * r.n_envs + env);
             env_reset(e, r, env, obs, (size_t)actor * r.n_envs + env);
         } else {
-            e.done = true; e.k = 0; e.ret = 0.0; e.t = 0.0; e.fault = 0; e.pv = &plant_pv[0][0]; e.theta_trim = 0.0;
+            e.done = true; e.k = 0; e.ret = 0.0; e.t = 0.0; e.fault = 0; e.pv = pv_base; e.theta_trim = 0.0;
             e.ref_lv = r.ref_levels; e.ref_st = r.ref_starts;
 #pragma unroll
             for (int i = 0; i < NX; ++i) e.X[i] = 0.0;
@@ -368,7 +429,7 @@ rollout_kernel_tc(TcArgs ar)
         }
         const size_t traj = (size_t)actor * r.n_envs + env;
         const bool replay = valid && r.replay != nullptr && env == r.replay_env;
-        while (__syncthreads_or(!e.done)) {
+        while (group_any(c.grp, !e.done)) {
             tc_actor_forward<ACT>(c, ar, tiles_actor, obs, a);
             if (!e.done) env_step(e, r, traj, actor, replay, a, obs);
         }
@@ -383,17 +444,18 @@ rollout_kernel_tc(TcArgs ar)
 
 // Actor.forward for a batch through the same tensor-core device code (parity tests of the GEMM path)
 template <int ACT>
-__global__ void __launch_bounds__(TC_THREADS, 2)
+__global__ void __launch_bounds__(2 * TC_THREADS, 1)
 actor_forward_tc_kernel(TcArgs ar)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bars[2 * TC_STAGES + 1];
     __shared__ uint32_t tmem_slot;
+    __shared__ uint32_t shared_state[4];
     TcCtx c;
-    tc_setup(c, ar, smem_raw, bars, &tmem_slot);
+    tc_setup(c, ar, smem_raw, bars, &tmem_slot, shared_state);
     tc_load_small(c, ar, 0);
-    const int tid = threadIdx.x;
-    for (int base = blockIdx.x * TC_THREADS; base < ar.n_obs; base += gridDim.x * TC_THREADS) {
+    const int tid = c.gtid;
+    for (int base = (blockIdx.x * 2 + c.grp) * TC_THREADS; base < ar.n_obs; base += 2 * gridDim.x * TC_THREADS) {
         const int i = base + tid;
         float obs[7], a[3];
 #pragma unroll
@@ -439,14 +501,16 @@ static int tc_prepare(TcArgs& ar, const float* d_weights, int pop, const int32_t
     const int w1 = widths[0], w2 = widths[1];
     if (w1 < 8 || w1 % 8 != 0 || w1 > 1024 || w2 < 8 || w2 > 320)
         return serl_fail(SERL_ERR_UNSUPPORTED, "wide actors: need w1 % 8 == 0, 8 <= w1 <= 1024, 8 <= w2 <= 320");
-    ar.w1 = w1; ar.w2 = w2; ar.n2pad = (w2 + 15) & ~15;
+    ar.w1_real = w1;
+    ar.w1 = (w1 + TC_KSLAB - 1) / TC_KSLAB * TC_KSLAB;
+    ar.w2 = w2; ar.n2pad = (w2 + 15) & ~15;
     int cols = 32;
     while (cols < ar.n2pad) cols <<= 1;
     ar.tmem_cols = cols;
-    ar.small_floats = (tc_small_floats(w1, ar.n2pad) + 3) & ~3;
-    ar.stage_floats = 2 * 2 * ar.n2pad * 4;
+    ar.small_floats = (tc_small_floats(ar.w1, ar.n2pad) + 3) & ~3;
+    ar.stage_floats = 2 * TC_CH * ar.n2pad * 4;
     const int P = (int)serl_actor_num_params_wide(widths, n_widths);
-    const int n_stages = w1 / TC_KSLAB;
+    const int n_stages = ar.w1 / TC_KSLAB;
     const size_t small_bytes = (size_t)pop * ar.small_floats * 4;
     const size_t tile_bytes = (size_t)pop * n_stages * ar.stage_floats * 4;
     void* scratch = nullptr;
@@ -457,11 +521,12 @@ static int tc_prepare(TcArgs& ar, const float* d_weights, int pop, const int32_t
     ar.small = small; ar.tiles = tiles;
     const long long total = (long long)pop * ((long long)ar.small_floats + (long long)n_stages * ar.stage_floats);
     const int grid = (int)((total + 255) / 256 < 8192 ? (total + 255) / 256 : 8192);
-    tc_layout_kernel<<<grid, 256, 0, s>>>(d_weights, pop, P, w1, w2, ar.n2pad, ar.small_floats, ar.stage_floats, small, tiles);
+    tc_layout_kernel<<<grid, 256, 0, s>>>(d_weights, pop, P, ar.w1, w1, w2, ar.n2pad, ar.small_floats, ar.stage_floats, small, tiles);
     serl_count_launch();
-    constexpr int A_STAGE_FLOATS = 2 * 2 * TC_THREADS * 4;
-    *smem_out = (size_t)(((ar.small_floats + 31) & ~31) + TC_STAGES * A_STAGE_FLOATS + TC_STAGES * ar.stage_floats) * 4;
-    if (*smem_out > 113 * 1024) return serl_fail(SERL_ERR_UNSUPPORTED, "wide actors: shared-memory ring exceeds half an SM");
+    constexpr int A_STAGE_FLOATS = 2 * TC_CH * TC_THREADS * 4;
+    *smem_out = (size_t)TC_TABN2 * sizeof(real) +
+                (size_t)(2 * ((ar.small_floats + 31) & ~31) + TC_STAGES * A_STAGE_FLOATS + TC_STAGES * ar.stage_floats) * 4;
+    if (*smem_out > 227 * 1024 - 256) return serl_fail(SERL_ERR_UNSUPPORTED, "wide actors: tables + parameters + rings exceed the shared memory of an SM");
     return SERL_OK;
 }
 
@@ -490,10 +555,10 @@ int rollout_tc_impl(const serl_rollout_desc& d, const int32_t* widths, int n_wid
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (d.sm_limit > 0 && d.sm_limit < sms) sms = d.sm_limit;
-    const long long grid = ar.n_tasks < 2LL * sms ? ar.n_tasks : 2LL * sms;
+    const long long grid = (ar.n_tasks + 1) / 2 < sms ? (ar.n_tasks + 1) / 2 : sms;
     cudaError_t e;
 #define TC_LAUNCH(A) do { e = cudaFuncSetAttribute(rollout_kernel_tc<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        if (e == cudaSuccess) { rollout_kernel_tc<A><<<(unsigned)grid, TC_THREADS, smem, s>>>(ar); e = cudaGetLastError(); } } while (0)
+        if (e == cudaSuccess) { rollout_kernel_tc<A><<<(unsigned)grid, 2 * TC_THREADS, smem, s>>>(ar); e = cudaGetLastError(); } } while (0)
     if (d.shape.activation == SERL_ACT_TANH) TC_LAUNCH(SERL_ACT_TANH);
     else if (d.shape.activation == SERL_ACT_ELU) TC_LAUNCH(SERL_ACT_ELU);
     else TC_LAUNCH(SERL_ACT_LEAKY_RELU);
@@ -515,10 +580,11 @@ extern "C" int serl_actor_forward_wide(const float* d_genome, const int32_t* wid
     int rc = tc_prepare(ar, d_genome, 1, widths, n_widths, s, &smem);
     if (rc != SERL_OK) return rc;
     ar.obs_in = d_obs; ar.act_out = d_actions; ar.n_obs = n;
-    const int grid = (n + TC_THREADS - 1) / TC_THREADS < 296 ? (n + TC_THREADS - 1) / TC_THREADS : 296;
+    const int blocks = (n + 2 * TC_THREADS - 1) / (2 * TC_THREADS);
+    const int grid = blocks < 148 ? blocks : 148;
     cudaError_t e;
 #define TC_LAUNCH(A) do { e = cudaFuncSetAttribute(actor_forward_tc_kernel<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        if (e == cudaSuccess) { actor_forward_tc_kernel<A><<<grid, TC_THREADS, smem, s>>>(ar); e = cudaGetLastError(); } } while (0)
+        if (e == cudaSuccess) { actor_forward_tc_kernel<A><<<grid, 2 * TC_THREADS, smem, s>>>(ar); e = cudaGetLastError(); } } while (0)
     if (activation == SERL_ACT_TANH) TC_LAUNCH(SERL_ACT_TANH);
     else if (activation == SERL_ACT_ELU) TC_LAUNCH(SERL_ACT_ELU);
     else TC_LAUNCH(SERL_ACT_LEAKY_RELU);
