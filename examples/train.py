@@ -25,6 +25,8 @@ parser.add_argument('-pop_size', default=10, type=int)
 parser.add_argument('-seed', type=int, default=7)
 parser.add_argument('-mut_type', type=str, default='normal')
 parser.add_argument('-test_ea', default=False, action='store_true')
+parser.add_argument('-use_distil', default=False, action='store_true')
+parser.add_argument('-distil_type', type=str, default='fitness')
 parser.add_argument('-sync_period', type=int, default=1)
 parser.add_argument('-num_envs', type=int, default=3)
 parser.add_argument('-hidden_size', type=int, default=72)

@@ -64,7 +64,8 @@ class Agent:
         self.champion = None
         self.champion_actor = None
         self.champion_history = None
-        self.store_population_transitions = args.frac_frames_train > 0 or getattr(args, 'mut_type', 'normal') in ('proximal', 'safe')
+        self.store_population_transitions = (args.frac_frames_train > 0 or getattr(args, 'mut_type', 'normal') in ('proximal', 'safe')
+                                             or bool(getattr(args, 'distil_crossover', False)))
         self._side = torch.cuda.Stream(self.device, priority=-1)
         self.speculative_validations = int(getattr(args, 'speculative_validations', 3))
         self._spec_streams = [torch.cuda.Stream(self.device, priority=-1) for _ in range(self.speculative_validations)]

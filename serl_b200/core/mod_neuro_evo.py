@@ -3,14 +3,15 @@
 Same constructor and `epoch(pop, fitness_evals, bcs_evals=None) -> int` contract; `pop` must be the engine's
 PopulationList (its genomes are mutated in place on the GPU).  Mutation operators: classic Gaussian point mutation
 ('normal' / 'inplace', K5) and the Jacobian-scaled 'proximal' / 'safe' mutations (:183-327) batched over the population
-(serl_b200/evo_prox.py, exact against the reference module).  Distillation crossover (:131-181, per-child behaviour-cloning
-training loops) is not implemented and raises, as the reference does for unknown operators (:38, :507).
+(serl_b200/evo_prox.py, exact against the reference module).  Crossover: the classic in-place operator (K4) or, with
+`distil_crossover`, the Q-filtered distillation crossover (:131-181) batched over all children (serl_b200/evo_distil.py;
+`distil_type` 'fitness'; other pairing rules raise NotImplementedError as the reference does for unknown ones, :507).
 """
 import random
 
 import torch
 
-from .. import evo, evo_prox
+from .. import evo, evo_distil, evo_prox
 
 
 class SSNE:
@@ -30,8 +31,10 @@ class SSNE:
             self._mut_gen = None
         else:
             raise ValueError('Mutation type is unknown!')
-        if getattr(self.args, 'distil_crossover', False):
-            raise NotImplementedError('distillation crossover is not part of the B200 hot path (SURVEY.md 8(f) N3)')
+        self.distil = bool(getattr(self.args, 'distil_crossover', False))
+        if self.distil and 'fitness' not in str(getattr(self.args, 'distil_type', 'fitness')).lower():
+            raise NotImplementedError("distillation crossover: only distil_type 'fitness' (mod_neuro_evo.py:498-499) is implemented")
+        self._gen = None
         self.last_plan = None
 
     def _selection_bookkeeping(self, elitist_index, offsprings, unselects):
@@ -51,10 +54,37 @@ class SSNE:
         if genomes is None:
             raise TypeError('SSNE.epoch needs the engine population (serl_b200.population.PopulationList)')
         classic = self.mutate is None
+        if self._gen is None:
+            self._gen = torch.Generator(device=genomes.device)
+            self._gen.manual_seed(int(getattr(self.args, 'seed', 7)) + 2)
+        fit_host = fitness_evals.detach().cpu().numpy() if torch.is_tensor(fitness_evals) else fitness_evals
+
+        def distil(plan):
+            # :497-513: one child per unselected actor, parents = the pairs of (new elitists + offsprings) ranked by
+            # summed fitness; all children of the generation are trained together
+            groups = evo_distil.sort_groups_by_fitness(plan.new_elitists + plan.offsprings, fit_host)
+            if not plan.distil_unselects or not groups:
+                return
+            first, second, bufs = [], [], []
+            for i, _ in enumerate(plan.distil_unselects):
+                a, b, _s = groups[i % len(groups)]
+                if fit_host[a] < fit_host[b]:
+                    a, b = b, a
+                first.append(int(a)); second.append(int(b))
+                bufs.append(evo_distil.child_buffer(pop, int(a), int(b), int(self.args.individual_bs) // 2, self._gen))
+            children = evo_distil.distil_children(genomes, first, second, bufs, pop.shape_tuple, self.args.activation_actor,
+                                                  self.critic, generator=self._gen)
+            idx = torch.as_tensor(plan.distil_unselects, dtype=torch.int64, device=genomes.device)
+            genomes[idx] = children                                          # clone(offspring, pop[unselected]) :513
+            for k, u in enumerate(plan.distil_unselects):                    # ... including the child's buffer (:378-382)
+                pop[u].buffer.reset()
+                pop[u].buffer.add_rows(bufs[k])
+                pop[u].critical_buffer.reset()
         elite, plan = evo.epoch_flat(genomes, fitness_evals, pop.shape_tuple,
                                      elite_fraction=self.args.elite_fraction, mutation_prob=self.args.mutation_prob,
                                      mutation_mag=self.args.mutation_mag, selection=self._selection_bookkeeping,
-                                     classic_mutation=classic)
+                                     classic_mutation=classic, classic_crossover=not self.distil,
+                                     between=distil if self.distil else None)
         self.last_plan = plan
         # clone() also copies the per-agent replay buffers (:377-382); host-side bookkeeping, in the reference's order
         for wave in plan.clone_waves:

@@ -46,10 +46,11 @@ def _waves(items, reads, writes):
 
 class EvoPlan:
     __slots__ = ('clone_waves', 'cross_waves', 'mut_seg', 'mut_off', 'mut_kind', 'mut_z', 'elite', 'new_elitists',
-                 'offsprings', 'unselects', 'n_cross_ops', 'timing', 'elitist_index', 'mut_candidates')
+                 'offsprings', 'unselects', 'n_cross_ops', 'timing', 'elitist_index', 'mut_candidates', 'distil_unselects')
 
 
-def plan_epoch(index_rank, offsprings_raw, table, population_size, num_elitists, mutation_prob, selection=None, native=False):
+def plan_epoch(index_rank, offsprings_raw, table, population_size, num_elitists, mutation_prob, selection=None, native=False,
+               classic_crossover=True):
     """Everything of SSNE.epoch after the tournaments, as op lists. `selection` (dict) receives rl-selection bookkeeping."""
     index_rank = [int(x) for x in index_rank]
     elitist_index = index_rank[:num_elitists]
@@ -78,7 +79,10 @@ def plan_epoch(index_rank, offsprings_raw, table, population_size, num_elitists,
         clones.append((i, replacee))
     plan.clone_waves = [np.asarray(w, dtype=np.int32).reshape(-1, 2)
                         for w in _waves(clones, lambda c: (c[0],), lambda c: (c[1],))]
-    # :516-523 classic crossover
+    # :516-523 classic crossover (the distillation branch :497-513 neither pads the list nor draws anything here)
+    plan.distil_unselects = list(unselects)
+    if not classic_crossover:
+        unselects = []
     if len(unselects) % 2 != 0:
         unselects.append(unselects[random.randrange(len(unselects))])
     plan.elite = new_elitists[0]
@@ -198,22 +202,24 @@ def select_device(fitness, num_elitists):
     return both[:pop], both[pop:]
 
 
-def apply_plan(weights, plan, mutation_mag):
+def apply_plan(weights, plan, mutation_mag, phase='all'):
+    """phase 'all', or 'pre' (elitism clones + crossover) / 'mut' (point mutations) when something runs in between
+    (distillation crossover writes the unselected genomes before they are mutated)."""
     L = _native.lib()
     dev = weights.device
     pop, P = weights.shape
     stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
     keep = []
-    for w in plan.clone_waves:
+    for w in (plan.clone_waves if phase in ('all', 'pre') else []):
         t = _dev(w, dev); keep.append(t)
         _native.check(L.serl_ssne_clone(_p(weights), pop, P, _p(t), w.shape[0], stream), 'serl_ssne_clone')
     d_ops = None
-    for desc, ops in plan.cross_waves:
+    for desc, ops in (plan.cross_waves if phase in ('all', 'pre') else []):
         if d_ops is None:
             d_ops = _dev(ops if ops.size else np.zeros((1, 3), np.int32), dev); keep.append(d_ops)
         t = _dev(desc, dev); keep.append(t)
         _native.check(L.serl_ssne_crossover(_p(weights), pop, P, _p(t), desc.shape[0], _p(d_ops), stream), 'serl_ssne_crossover')
-    if plan.mut_seg.shape[0]:
+    if plan.mut_seg.shape[0] and phase in ('all', 'mut'):
         seg, off, kind, z = (_dev(a, dev) for a in (plan.mut_seg, plan.mut_off, plan.mut_kind, plan.mut_z))
         keep += [seg, off, kind, z]
         mag32 = ctypes.c_float(float(np.float32(mutation_mag)))
@@ -224,7 +230,7 @@ def apply_plan(weights, plan, mutation_mag):
 
 
 def epoch_flat(weights, fitness, shape, elite_fraction=0.2, mutation_prob=0.9, mutation_mag=0.0247682869654, selection=None,
-               classic_mutation=True):
+               classic_mutation=True, classic_crossover=True, between=None):
     """One generation on device genomes. weights [pop,P] fp32 cuda (modified in place); fitness: cuda f64 tensor or array-like.
     shape = (state_dim, action_dim, hidden, num_layers). Returns (new elite index, plan)."""
     if not weights.is_cuda:
@@ -243,10 +249,16 @@ def epoch_flat(weights, fitness, shape, elite_fraction=0.2, mutation_prob=0.9, m
     t1 = time.perf_counter()
     # classic_mutation=False (proximal / safe mutation, core/mod_neuro_evo.py): the planner emits no Gaussian point
     # mutations and consumes no draws for them; the caller draws the per-actor decisions itself, in the reference's order
-    plan = plan_epoch(index_rank, offs_raw, table, pop, num_elitists, mutation_prob if classic_mutation else -1.0, selection, native=True)
+    plan = plan_epoch(index_rank, offs_raw, table, pop, num_elitists, mutation_prob if classic_mutation else -1.0, selection, native=True,
+                      classic_crossover=classic_crossover)
     plan.mut_candidates = [int(i) for i in index_rank[num_elitists:]]
     t2 = time.perf_counter()
-    apply_plan(weights, plan, mutation_mag)
+    if between is None:
+        apply_plan(weights, plan, mutation_mag)
+    else:          # e.g. distillation crossover: after the elitism clones, before the mutations
+        apply_plan(weights, plan, mutation_mag, phase='pre')
+        between(plan)
+        apply_plan(weights, plan, mutation_mag, phase='mut')
     t3 = time.perf_counter()
     plan.timing = {'select_ms': 1e3 * (t1 - t0), 'plan_ms': 1e3 * (t2 - t1), 'apply_ms': 1e3 * (t3 - t2),
                    'mutations': int(plan.mut_off.shape[0]), 'crossover_copies': int(plan.n_cross_ops)}

@@ -61,8 +61,8 @@ class Parameters:
             self.mutation_batch_size = self.batch_size
             self.mut_type = g('mut_type', 'normal')
             # 'proximal' (base/train.py's CLI default) and 'safe' are implemented batched on the device (serl_b200/evo_prox.py)
-            self.distil_crossover = False
-            self.distil_type = g('distil_type', 'distance')
+            self.distil_crossover = bool(g('use_distil', False))      # the reference hard-codes True (parameters.py:112)
+            self.distil_type = g('distil_type', 'fitness')
             self.crossover_prob = 0.0
             self._verbose_mut = g('verbose_mut', False)
             self._verbose_crossover = g('verbose_crossover', False)

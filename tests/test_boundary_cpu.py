@@ -49,7 +49,9 @@ def test_ssne_rejects_out_of_scope_operators():
     args = make_args()
     args.mut_type = 'proximal'
     assert SSNE(args, None, None).mutate == 'proximal'        # batched on the device (serl_b200/evo_prox.py)
-    args.distil_crossover = True
+    args.distil_crossover, args.distil_type = True, 'fitness'
+    assert SSNE(args, None, None).distil                      # batched on the device (serl_b200/evo_distil.py)
+    args.distil_type = 'distance'
     with pytest.raises(NotImplementedError):
         SSNE(args, None, None)
     args.distil_crossover = False

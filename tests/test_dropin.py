@@ -68,6 +68,19 @@ def test_launcher_with_the_reference_default_proximal_mutation(tmp_path):
     check_checkpoints(tmp_path / 'tmp')
 
 
+@pytest.mark.gpu
+def test_launcher_with_distillation_crossover_and_safe_mutation(tmp_path):
+    """the reference's shipped operator set (SERL50 config.yaml: mut_type safe, distil_type fitness): Q-filtered distillation
+    crossover and the safe mutation, both batched on the device."""
+    args = ['-frames', '9000', '-pop_size', '8', '-mut_type', 'safe', '-use_distil', '-distil_type', 'fitness', '-test_ea']
+    p = subprocess.run([sys.executable, os.path.join(ROOT, 'examples', 'train.py')] + args, cwd=tmp_path, capture_output=True, text=True,
+                       timeout=1800)
+    assert p.returncode == 0, p.stderr[-3000:]
+    pop = torch.load(os.path.join(tmp_path, 'tmp', 'evo_nets.pkl'), weights_only=False)
+    assert sorted(pop) == ['actor_%d' % i for i in range(8)]
+    assert all(torch.isfinite(v).all() for v in pop['actor_3'].values())
+
+
 def test_proximal_default_of_train_py_is_kept():
     """base/train.py's CLI default is -mut_type proximal: implemented (serl_b200/evo_prox.py), so Parameters keeps it."""
     import types

@@ -95,3 +95,60 @@ def test_batched_proximal_mutation_equals_the_reference_module(tmp_path, monkeyp
     evo_prox.proximal_mutate_batched(G2, [0, 1, 2], states, shape, args.activation_actor, args.mutation_mag, delta=torch.stack(deltas))
     assert (G_ref - G).abs().max() > 0.1
     assert (G2 - G_ref).abs().max().item() <= 1e-6
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason='needs the reference tree (build container only)')
+def test_batched_distillation_step_equals_the_reference_update_parameters(tmp_path, monkeypatch):
+    """one Q-filtered behaviour-cloning Adam step (base/core/genetic_agent.py:22-60) for three children at once."""
+    from serl_b200 import evo_distil
+    monkeypatch.chdir(tmp_path)
+    saved = {k: sys.modules.pop(k) for k in list(sys.modules) if k == 'core' or k.startswith('core.') or k == 'parameters'}
+    sys.path.insert(0, REF)
+    try:
+        from core import genetic_agent as ref_ga
+        from parameters import Parameters as RefP
+        args = RefP(types.SimpleNamespace(pop_size=4, mut_type='proximal', env='x', frames=1, seed=1, disable_cuda=True))
+        args.state_dim, args.action_dim, args.device = 7, 3, torch.device('cpu')
+        torch.manual_seed(0)
+        kids = [ref_ga.GeneticAgent(args) for _ in range(3)]
+        p1s = [ref_ga.GeneticAgent(args) for _ in range(3)]
+        p2s = [ref_ga.GeneticAgent(args) for _ in range(3)]
+        flat = lambda g: torch.cat([p.data.reshape(-1) for p in g.actor.parameters()])
+        lin = torch.nn.Linear(10, 2)
+
+        def critic(s, a):
+            q = lin(torch.cat((s, a), 1))
+            return q[:, :1], q[:, 1:]
+        states = torch.randn(3, 40, 7) * 0.2
+        shape = (7, 3, args.hidden_size, args.num_layers)
+        G0 = torch.stack([flat(k) for k in kids])
+        G1, G2 = torch.stack([flat(p) for p in p1s]), torch.stack([flat(p) for p in p2s])
+        mse_ref = [kids[c].update_parameters((states[c], None, None, None, None), p1s[c].actor, p2s[c].actor, critic) for c in range(3)]
+        G_ref = torch.stack([flat(k) for k in kids])
+    finally:
+        sys.path.remove(REF)
+        for k in [k for k in sys.modules if k == 'core' or k.startswith('core.') or k == 'parameters']:
+            del sys.modules[k]
+        sys.modules.update(saved)
+    child = G0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([child], lr=1e-3)
+    with torch.no_grad():
+        a1 = evo_prox.actor_forward_batched(G1, states, shape, 'tanh')
+        a2 = evo_prox.actor_forward_batched(G2, states, shape, 'tanh')
+        fl = states.reshape(120, 7)
+        q1 = torch.min(*critic(fl, a1.reshape(120, 3))).reshape(3, 40)
+        q2 = torch.min(*critic(fl, a2.reshape(120, 3))).reshape(3, 40)
+    opt.zero_grad()
+    loss, mse = evo_distil.cloning_loss(evo_prox.actor_forward_batched(child, states, shape, 'tanh'), a1, a2, q1, q2)
+    loss.backward()
+    opt.step()
+    assert (G_ref - G0).abs().max() > 1e-4
+    assert (child.detach() - G_ref).abs().max().item() <= 2e-6
+    assert np.allclose(mse.numpy(), np.asarray(mse_ref), rtol=1e-4)
+
+
+def test_sort_groups_by_fitness_order():
+    from serl_b200 import evo_distil
+    fit = {3: -10.0, 5: -2.0, 9: -7.0}
+    g = evo_distil.sort_groups_by_fitness([3, 5, 9], fit)
+    assert g[0][:2] == (5, 9) and g[-1][:2] == (9, 3) and g[0][2] == -9.0
