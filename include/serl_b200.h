@@ -27,8 +27,15 @@ enum { SERL_ACT_TANH = 0, SERL_ACT_ELU = 1, SERL_ACT_LEAKY_RELU = 2 };
 
 /* plant variants = the reference's distinct native builds envs/<variant>/_citation*.so */
 enum { SERL_PLANT_H2000_V90 = 0, SERL_PLANT_ICE = 1, SERL_PLANT_CG = 2, SERL_PLANT_CG_FOR = 3,
-       SERL_PLANT_H2000_V150 = 4, SERL_PLANT_H10000_V90 = 5, SERL_PLANT_COUNT = 6 };
-/* command faults = envs/{be,jr,sa,se}/citation.py:71-79; env_mode = variant | (fault << 8) */
+       SERL_PLANT_H2000_V150 = 4, SERL_PLANT_H10000_V90 = 5,
+       SERL_PLANT_CG_TIMED = 6,        /* envs/cg_timed before its trigger (= the nominal dynamics) */
+       SERL_PLANT_CG_TIMED_POST = 7,   /* ... and once the model clock has reached 20 s (envs/phlabenv.py:159-163) */
+       SERL_PLANT_COUNT = 8 };
+/* command faults = envs/{be,jr,sa,se}/citation.py:71-79; env_mode = variant | (fault << 8) | (post_variant << 16):
+ * post_variant != 0 is the parameter row the plant switches to when its clock reaches SERL_TRIGGER_CALLS * 0.01 s (the
+ * time-triggered build cg_timed: variant 6, post_variant 7); the switch happens inside the ode5 step whose last stage
+ * reaches 20 s, exactly as in the reference binary */
+#define SERL_TRIGGER_CALLS 2000
 enum { SERL_FAULT_NONE = 0, SERL_FAULT_BE = 1, SERL_FAULT_JR = 2, SERL_FAULT_SA = 3, SERL_FAULT_SE = 4 };
 
 #define SERL_REF_BLOCKS 6   /* reference-signal blocks per channel (oracle/refsig.py) */
@@ -143,6 +150,9 @@ int serl_smoothness(const float* d_actions, const int32_t* d_steps, int32_t n_tr
  * psi, x_e, y_e are not integrated (they never feed back) and keep their initial values. */
 int serl_plant_init(double* d_X, const int32_t* d_variant, int32_t n, void* stream);
 int serl_plant_step(double* d_X, const double* d_cmd, const int32_t* d_variant, int32_t n, void* stream);
+/* the same for time-triggered builds: d_variant[i] = variant | post_variant << 16, d_call[i] = number of native step() calls the
+ * model has already made since initialize() (its clock in units of 0.01 s) */
+int serl_plant_step_timed(double* d_X, const double* d_cmd, const int32_t* d_variant, const int32_t* d_call, int32_t n, void* stream);
 
 /* ---- neuro-evolution (base/core/mod_neuro_evo.py, classic operators) -------------------------------------
  * All random draws are made on the host in the reference's order; the device applies compact op lists.

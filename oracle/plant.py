@@ -23,6 +23,7 @@ MODES = {
     'nominal': ('h2000_v90', 'none'), 'be': ('h2000_v90', 'be'), 'jr': ('h2000_v90', 'jr'),
     'sa': ('h2000_v90', 'sa'), 'se': ('h2000_v90', 'se'), 'ice': ('ice', 'none'), 'cg': ('cg', 'none'),
     'cg-for': ('cg_for', 'none'), 'h2000-v150': ('h2000_v150', 'none'), 'h10000-v90': ('h10000_v90', 'none'),
+    'cg-timed': ('cg_timed', 'none'),       # time-triggered build: reference binary only, one episode at a time (own clock)
 }
 FAULTS = ['none', 'be', 'jr', 'sa', 'se']
 
@@ -62,6 +63,7 @@ class RefPlant:
         self.ic = np.array(self.rtX[:], dtype=np.float64)
 
     def initial_state(self):
+        self.lib.initialize()          # also resets the model clock (time-triggered builds)
         return self.ic.copy()
 
     def step(self, X, cmd10):
@@ -104,6 +106,8 @@ class PortPlant:
 
 
 def make_plant(variant, backend='auto'):
+    if variant in _build.REF_ONLY:
+        backend = 'ref'
     if backend == 'auto':
         backend = 'ref' if _build.have_ref() else 'port'
     return RefPlant(variant) if backend == 'ref' else PortPlant(variant)

@@ -58,6 +58,8 @@ def lib():
         L.serl_actor_num_params_wide.argtypes = [vp, i32]
         L.serl_actor_forward_wide.restype = ctypes.c_int
         L.serl_actor_forward_wide.argtypes = [vp, vp, i32, i32, vp, i32, vp, vp]
+        L.serl_plant_step_timed.restype = ctypes.c_int
+        L.serl_plant_step_timed.argtypes = [vp, vp, vp, vp, i32, vp]
         L.serl_smoothness.restype = ctypes.c_int
         L.serl_smoothness.argtypes = [vp, vp, i32, i32, ctypes.c_double, vp, vp]
         L.serl_launch_count.restype = i64

@@ -198,7 +198,11 @@ static __device__ __noinline__ void plant_step_nav(double* Xnav, const double* X
 // is ONE __noinline__ function (the same code for every plant variant), so the compact state x[14] and the stage
 // derivatives f[6][14] live in local memory (896 B per thread, L1-resident).  The integrator state and the stage
 // combinations are double in every build; `real` (the type of the right-hand side) is double unless PLANT_F32.
-static __device__ __noinline__ void plant_step(const real* pv, double* X, const double* U, const real* tab, bool nav = false)
+// pv_post / call: time-triggered builds (cg_timed): the parameter row switches to pv_post when the model clock
+// call * 0.01 + c_s * 0.01 of a stage reaches 20 s: every stage from call SERL_TRIGGER_CALLS on, and the LAST stage (c = 1) of
+// call SERL_TRIGGER_CALLS - 1, whose time 19.99 + 0.01 already compares >= 20 in the binary.
+static __device__ __noinline__ void plant_step(const real* pv, double* X, const double* U, const real* tab, bool nav = false,
+                                               const real* pv_post = nullptr, int call = 0)
 {
     constexpr double h = 0.01;
     constexpr double B[6][6] = ODE5_B_INIT;
@@ -210,7 +214,8 @@ static __device__ __noinline__ void plant_step(const real* pv, double* X, const 
     double xl[NLIVE];
 #pragma unroll
     for (int s = 0; s < 6; ++s) {
-        plant_rhs_common(x, u, f[s], tab, pv);
+        const bool post = pv_post != nullptr && (call >= SERL_TRIGGER_CALLS || (s == 5 && call == SERL_TRIGGER_CALLS - 1));
+        plant_rhs_common(x, u, f[s], tab, post ? pv_post : pv);
 #pragma unroll
         for (int li = 0; li < NLIVE; ++li) {
             double acc = (double)f[0][li] * (h * B[s][0]);
@@ -285,6 +290,7 @@ struct Env {
     double X[NX];
     const real* tab;         // plant tables (shared or global memory)
     const real* pv;          // parameter row of this env's plant variant
+    const real* pv_post;     // row after the trigger of a time-triggered build, or nullptr
     const double* ref_lv;    // this env's reference-signal levels / starts [2][SERL_REF_BLOCKS] (global, read per step)
     const double* ref_st;
     double t, ret, theta_trim;
@@ -310,6 +316,8 @@ __device__ __forceinline__ void env_bind(Env& e, const RolloutArgs& a, int env, 
     const int mode = a.env_mode[env];
     const int variant = mode & 0xff;
     e.pv = pv_base + variant * PLANT_NPV;
+    const int post = (mode >> 16) & 0xff;
+    e.pv_post = post ? pv_base + post * PLANT_NPV : nullptr;
     e.fault = (mode >> 8) & 0xff;
     e.ref_lv = a.ref_levels + (size_t)env * 2 * SERL_REF_BLOCKS;
     e.ref_st = a.ref_starts + (size_t)env * 2 * SERL_REF_BLOCKS;
@@ -349,7 +357,7 @@ static __device__ void env_reset(Env& e, const RolloutArgs& a, int env, float* o
     obs[3] = (float)x0[0]; obs[4] = (float)x0[1]; obs[5] = (float)x0[2]; obs[6] = (float)x0[4];
     double U[3] = {0.0, 0.0, 0.0}, cmd[3];
     apply_fault(e.fault, U, cmd);
-    plant_step(e.pv, e.X, cmd, e.tab, a.trace != nullptr);
+    plant_step(e.pv, e.X, cmd, e.tab, a.trace != nullptr, e.pv_post, 0);
     e.t = 0.0; e.ret = 0.0; e.k = 0; e.done = false;
 }
 
@@ -385,7 +393,7 @@ static __device__ void env_step(Env& e, const RolloutArgs& ar, size_t traj, int 
     double xo[12];
 #pragma unroll
     for (int i = 0; i < 12; ++i) xo[i] = e.X[i];
-    plant_step(e.pv, e.X, cmd, e.tab, ar.trace != nullptr);
+    plant_step(e.pv, e.X, cmd, e.tab, ar.trace != nullptr, e.pv_post, e.k + 1);
     sensor_noise(ar, traj, e.k + 1, xo);
 
     const double t = e.t;

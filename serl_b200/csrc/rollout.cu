@@ -389,7 +389,7 @@ rollout_kernel_persist(RolloutArgs ar)
                 env_reset(e, ar, env, obs, (size_t)actor * ar.n_envs + env);
             }
         } else {
-            e.done = true; e.k = 0; e.ret = 0.0; e.t = 0.0; e.fault = 0; e.pv = pv_base; e.theta_trim = 0.0;
+            e.done = true; e.k = 0; e.ret = 0.0; e.t = 0.0; e.fault = 0; e.pv = pv_base; e.pv_post = nullptr; e.theta_trim = 0.0;
             e.ref_lv = ar.ref_levels; e.ref_st = ar.ref_starts;
 #pragma unroll
             for (int i = 0; i < NX; ++i) e.X[i] = 0.0;
@@ -510,7 +510,8 @@ __global__ void fitness_mean_kernel(const double* __restrict__ returns, int pop,
 }
 
 // batched native-plant step: X[n,19] advanced in place by one major step with command cmd[n,3] (inputs 3..9 are 0)
-__global__ void plant_step_kernel(double* __restrict__ X, const double* __restrict__ cmd, const int* __restrict__ variant, int n)
+__global__ void plant_step_kernel(double* __restrict__ X, const double* __restrict__ cmd, const int* __restrict__ variant,
+                                  const int* __restrict__ call, int n)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -518,7 +519,8 @@ __global__ void plant_step_kernel(double* __restrict__ X, const double* __restri
 #pragma unroll
     for (int k = 0; k < NX; ++k) x[k] = X[(size_t)i * NX + k];
     u[0] = cmd[3 * i]; u[1] = cmd[3 * i + 1]; u[2] = cmd[3 * i + 2];
-    plant_step(plant_pv[variant[i] & 0xff], x, u, plant_tables_blob);
+    const int post = (variant[i] >> 16) & 0xff;
+    plant_step(plant_pv[variant[i] & 0xff], x, u, plant_tables_blob, false, post ? plant_pv[post] : nullptr, call ? call[i] : 0);
 #pragma unroll
     for (int k = 0; k < NX; ++k) X[(size_t)i * NX + k] = x[k];
 }
@@ -543,7 +545,16 @@ extern "C" int serl_plant_init(double* d_X, const int32_t* d_variant, int32_t n,
 extern "C" int serl_plant_step(double* d_X, const double* d_cmd, const int32_t* d_variant, int32_t n, void* stream)
 {
     if (!d_X || !d_cmd || !d_variant || n <= 0) return serl_fail(SERL_ERR_ARG, "serl_plant_step: bad argument");
-    plant_step_kernel<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(d_X, d_cmd, d_variant, n);
+    plant_step_kernel<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(d_X, d_cmd, d_variant, nullptr, n);
+    serl_count_launch();
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? SERL_OK : serl_fail_cuda(e, "plant_step_kernel");
+}
+
+extern "C" int serl_plant_step_timed(double* d_X, const double* d_cmd, const int32_t* d_variant, const int32_t* d_call, int32_t n, void* stream)
+{
+    if (!d_X || !d_cmd || !d_variant || !d_call || n <= 0) return serl_fail(SERL_ERR_ARG, "serl_plant_step_timed: bad argument");
+    plant_step_kernel<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(d_X, d_cmd, d_variant, d_call, n);
     serl_count_launch();
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? SERL_OK : serl_fail_cuda(e, "plant_step_kernel");

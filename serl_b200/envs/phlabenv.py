@@ -47,14 +47,14 @@ class CitationEnv:
         m = mode.lower()
         if m == '' or m == 'nominal' or 'h2000-v90' in m:
             m = 'nominal'
-        alias = {'high-q': 'h2000-v150', 'low-q': 'h10000-v90', 'cg-aft': 'cg'}
+        alias = {'high-q': 'h2000-v150', 'low-q': 'h10000-v90', 'cg-aft': 'cg', 'cg-shift': 'cg-timed'}
         m = alias.get(m, m)
         # 'noise' (envs/phlabenv.py:139-142): the nominal plant behind the sensor-noise shim (envs/noise/citation.py:72-82)
         self.sensor_noise = m == 'noise'
         if self.sensor_noise:
             m = 'nominal'
-        if m in ('gust', 'cg-timed', 'cg-shift', 'test'):
-            raise ValueError("mode '%s': the time-triggered plant builds (gust / cg_timed / test) are not lifted (DESIGN.md: out of scope)" % m)
+        if m in ('gust', 'test'):
+            raise ValueError("mode '%s': the gust / test plant builds are not lifted (DESIGN.md: out of scope)" % m)
         if m not in rollout.MODES:
             raise ValueError('Unknown trim condition or control mode!')
         self.mode = m
@@ -173,8 +173,15 @@ class CitationEnv:
             x[5] += 1.8 * 10**(-3) + 2.7 * 10**(-4) * np.random.randn(1)[0]
             x[6:8] += 4.0 * 10**(-3) + 3.2 * 10**(-5) * np.random.randn(2)
         dcmd = torch.as_tensor(cmd[:3].reshape(1, 3), device=self._X.device)
-        self._plant('serl_plant_step', ctypes.c_void_p(self._X.data_ptr()), ctypes.c_void_p(dcmd.data_ptr()),
-                    ctypes.c_void_p(self._variant.data_ptr()), 1)
+        if self.mode_code >> 16:          # time-triggered build: the plant needs its clock (native calls made so far)
+            call = torch.tensor([self._calls], dtype=torch.int32, device=self._X.device)
+            var = torch.tensor([(self.mode_code & 0xff) | (self.mode_code & 0xff0000)], dtype=torch.int32, device=self._X.device)
+            self._plant('serl_plant_step_timed', ctypes.c_void_p(self._X.data_ptr()), ctypes.c_void_p(dcmd.data_ptr()),
+                        ctypes.c_void_p(var.data_ptr()), ctypes.c_void_p(call.data_ptr()), 1)
+        else:
+            self._plant('serl_plant_step', ctypes.c_void_p(self._X.data_ptr()), ctypes.c_void_p(dcmd.data_ptr()),
+                        ctypes.c_void_p(self._variant.data_ptr()), 1)
+        self._calls += 1
         return x
 
     def reset(self, **kwargs):
@@ -186,6 +193,7 @@ class CitationEnv:
         self._X = torch.empty((1, 19), dtype=torch.float64, device=dev)
         self._plant('serl_plant_init', ctypes.c_void_p(self._X.data_ptr()), ctypes.c_void_p(self._variant.data_ptr()), 1)
         self.last_u = np.zeros(self.n_actions)
+        self._calls = 0
         self.x = self._native_step(self.last_u)
         self.V0 = self.V
         self.init_ref(**kwargs)

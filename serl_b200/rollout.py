@@ -10,19 +10,23 @@ import torch
 from . import _native
 
 HORIZON = 2001          # envs/phlabenv.py:82,181,392: t_max = 20 s, dt = 0.01, done checked before t += dt
-PLANT_VARIANTS = ['h2000_v90', 'ice', 'cg', 'cg_for', 'h2000_v150', 'h10000_v90']
+PLANT_VARIANTS = ['h2000_v90', 'ice', 'cg', 'cg_for', 'h2000_v150', 'h10000_v90', 'cg_timed', 'cg_timed_post']
+# time-triggered builds: parameter row the plant switches to when its clock reaches 20 s (envs/phlabenv.py:159-163)
+POST_VARIANT = {'cg_timed': 'cg_timed_post'}
 FAULTS = ['none', 'be', 'jr', 'sa', 'se']
 # env mode string (envs/phlabenv.py:99-172) -> (plant variant, command fault)
 MODES = {
     'nominal': ('h2000_v90', 'none'), 'be': ('h2000_v90', 'be'), 'jr': ('h2000_v90', 'jr'),
     'sa': ('h2000_v90', 'sa'), 'se': ('h2000_v90', 'se'), 'ice': ('ice', 'none'), 'cg': ('cg', 'none'),
     'cg-for': ('cg_for', 'none'), 'h2000-v150': ('h2000_v150', 'none'), 'h10000-v90': ('h10000_v90', 'none'),
+    'cg-timed': ('cg_timed', 'none'),
 }
 
 
 def mode_code(mode):
     v, f = MODES[mode]
-    return PLANT_VARIANTS.index(v) | (FAULTS.index(f) << 8)
+    post = PLANT_VARIANTS.index(POST_VARIANT[v]) if v in POST_VARIANT else 0
+    return PLANT_VARIANTS.index(v) | (FAULTS.index(f) << 8) | (post << 16)
 
 
 def actor_shape(hidden, num_layers=3, activation='tanh', state_dim=7, action_dim=3):

@@ -100,5 +100,42 @@ def test_calc_nmae_literal():
 def test_noise_mode_and_time_triggered_modes_are_named():
     from serl_b200.envs import config
     assert config.select_env('PHlab_attitude_noise').sensor_noise
+    assert config.select_env('PHlab_attitude_cg-shift').mode == 'cg-timed'
     with pytest.raises(ValueError):
         config.select_env('PHlab_attitude_gust')
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'oracle', '_ref', 'citation_cg_timed.so')),
+                    reason='needs the reference cg_timed binary under oracle/_ref')
+def test_cg_timed_build_switches_at_20_s_like_the_reference_binary():
+    """envs/cg_timed ('CG Aft after 20s', envs/phlabenv.py:159-163): nominal dynamics until the model clock reaches 20 s — in the
+    LAST ode5 stage of native call 1999 — then three moment-arm parameters change.  40 s episodes (4001 steps) through the
+    kernel vs the reference binary stepped by the oracle env; also the plain cg and nominal modes must differ from it."""
+    from serl_b200 import rollout
+    dev = torch.device('cuda:0')
+    g = ACT['serl10_elite_h72_tanh']
+    lv, st = refsig.make_ref_params(1, seed_base=40, t_max=40)
+    md = lambda m: torch.tensor([rollout.mode_code(m)], dtype=torch.int32, device=dev)
+    run = lambda m: rollout.population_rollout(torch.as_tensor(g[None], device=dev), rollout.actor_shape(72), torch.as_tensor(lv, device=dev),
+                                               torch.as_tensor(st, device=dev), md(m), horizon=4001, trace=True, t_max=40.0, smooth_width=6.0)
+    r = run('cg-timed')
+    torch.cuda.synchronize()
+    r.check()
+    env = phlab.CitationEnv('cg-timed', 'ref', t_max=40)
+    env.smooth_w = 6.0
+    obs = env.reset(lv[0], st[0])
+    tot, xs = 0.0, []
+    for k in range(4001):
+        obs, rew, done, _ = env.step(KOActor(g).select_action(obs))
+        xs.append(env.x.copy())
+        tot += rew
+        if done:
+            break
+    assert int(r.steps[0, 0]) == k + 1 == 4001
+    tx = r.trace_x[0, 0, :k + 1].cpu().numpy()
+    live = [0, 1, 2, 3, 4, 5, 6, 7, 9]
+    assert np.abs(tx[:, live] - np.asarray(xs)[:, live]).max() < 1e-8
+    assert abs(float(r.returns[0, 0]) - tot) <= 1e-8 * abs(tot)
+    nominal = run('nominal')
+    assert np.array_equal(nominal.trace_x[0, 0, :1999].cpu().numpy()[:, live], tx[:1999, live])        # identical before the trigger
+    assert np.abs(nominal.trace_x[0, 0, 2100:2400].cpu().numpy()[:, live] - tx[2100:2400, live]).max() > 1e-5

@@ -26,9 +26,9 @@ typedef %(real)s real;
 #define PLANT_TAB(name) (plant_tab + PT_OFF_##name)
 #define PLANT_CONSTS(n) static const real plant_k[n]
 #define PLANT_K(i) plant_k[i]
-#define PLANT_IC_TABLE static const double plant_ic_table[6][19]
+#define PLANT_IC_TABLE static const double plant_ic_table[8][19]
 #define PLANT_IC(v) static const double plant_ic_unused_##v[19]
-#define PLANT_PV_TABLE static const real plant_pv[6][PLANT_NPV]
+#define PLANT_PV_TABLE static const real plant_pv[8][PLANT_NPV]
 #define PLANT_PV(k) plant_pvrow[k]
 #define PLANT_XI(i) (i)
 #define PLANT_DIV(a, b) ((a) / (b))

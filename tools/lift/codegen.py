@@ -9,6 +9,8 @@ first argument is a constant collapses to a 1-D lookup over a pre-blended column
 pre-divided in double with the reference's operation order so results stay bit-identical); sharing of
 the breakpoint search between lookups on the same (axis, input).
 """
+import math
+
 import symtrace as S
 
 
@@ -186,6 +188,11 @@ class Emitter:
                 L.append('const %s %s = %s * %s;' % (R, v, r(a[0]), self.lit(1.0 / S.fval(a[1].args[0]))))   # x / c -> x * (1/c)
             elif op == 'div' and self.fast:
                 L.append('const %s %s = PLANT_DIV(%s, %s);' % (R, v, r(a[0]), r(a[1])))
+            elif op == 'sub' and a[0].op == 'const' and S.fval(a[0].args[0]) == 0.0 and math.copysign(1.0, S.fval(a[0].args[0])) < 0:
+                L.append('const %s %s = -%s;' % (R, v, r(a[1])))       # -0.0 - x: a negation (one build negates by subtraction ...
+            elif op == 'mul' and any(x.op == 'const' and S.fval(x.args[0]) == -1.0 for x in a[:2]):
+                other = a[1] if (a[0].op == 'const' and S.fval(a[0].args[0]) == -1.0) else a[0]
+                L.append('const %s %s = -%s;' % (R, v, r(other)))      # ... another by a gain of -1): the same bits either way
             elif op in ('add', 'sub', 'mul', 'div'):
                 sym = {'add': '+', 'sub': '-', 'mul': '*', 'div': '/'}[op]
                 L.append('const %s %s = %s %s %s;' % (R, v, r(a[0]), sym, r(a[1])))

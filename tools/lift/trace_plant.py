@@ -8,9 +8,20 @@ SIMTIMESTEP_OFF = 0xba48     # rtM_.Timing.simTimeStep (step @0x6060 reads rtM_+
 DERIVS_OFF = 46416           # rtM_.derivs
 
 
-def trace(so, nsym_u=3, verbose=False, assume=None, concrete=()):
+# model time inside rtM_ (found by stepping the cg_timed build and scanning rtM_: two doubles that read k*0.01 after k steps,
+# two uint32 tick counters); poked to trace the right-hand side AFTER a time-triggered switch (cg_timed: t >= 20 s)
+TIME_DOUBLES, TIME_TICKS = (64, 47808), (47640, 47656)
+
+
+def trace(so, nsym_u=3, verbose=False, assume=None, concrete=(), t_poke=None):
     img = S.Image(so, '/tmp/lift')
     img.lib.initialize()
+    if t_poke is not None:
+        base = img.addr('rtM_')
+        for off in TIME_DOUBLES:
+            ctypes.c_double.from_address(base + off).value = float(t_poke)
+        for off in TIME_TICKS:
+            ctypes.c_uint32.from_address(base + off).value = int(round(t_poke / 0.01))
     st = S.State(img)
     stack = ctypes.create_string_buffer(1 << 20)
     st.g[4] = (ctypes.addressof(stack) + (1 << 20) - 65536) & ~0xf
