@@ -39,6 +39,12 @@ class _Flight:
     __slots__ = ('r', 'levels', 'starts', 'n', 'noise_state', 'stream', 'event', 'keep')
 
 
+class _Front:
+    """the launches a generation starts with: RL exploration / validation flights, speculative champion validations, the
+    population rollout — and the signature of what they read."""
+    __slots__ = ('signature', 'f_explore', 'f_rlval', 'spec', 'val_draws', 'pop')
+
+
 class Agent:
     def __init__(self, args, environment):
         self.args = args
@@ -66,8 +72,14 @@ class Agent:
         self.champion_history = None
         self.store_population_transitions = (args.frac_frames_train > 0 or getattr(args, 'mut_type', 'normal') in ('proximal', 'safe')
                                              or bool(getattr(args, 'distil_crossover', False)))
-        self._side = torch.cuda.Stream(self.device, priority=-1)
-        self.speculative_validations = int(getattr(args, 'speculative_validations', 3))
+        # single-actor flights run next to the population rollout, each on its own high-priority stream and spare SM
+        self._side, self._side2, self._champ = (torch.cuda.Stream(self.device, priority=-1) for _ in range(3))
+        # launch the next generation's rollouts at the end of train() (see there); False = strictly one generation per call
+        self.prefetch_generation = bool(getattr(args, 'prefetch_generation', True))
+        self._prefetched = None
+        # speculative validation of last generation's elites hides the champion's validation latency INSIDE a generation;
+        # with the next generation's front launched ahead it is hidden anyway, and the spare SMs go to the population
+        self.speculative_validations = int(getattr(args, 'speculative_validations', 0 if self.prefetch_generation else 3))
         self._spec_streams = [torch.cuda.Stream(self.device, priority=-1) for _ in range(self.speculative_validations)]
         self.spec_hits = self.spec_tries = 0
         self.timing = {}
@@ -145,14 +157,24 @@ class Agent:
     def _collect(self, agent, f: _Flight, store_transition=False, want_history=False):
         """wait for a flight and rebuild the reference's per-episode records: list of Episode."""
         f.event.synchronize()
-        f.r.check()
-        steps = f.r.steps[0].cpu().numpy()
-        returns = f.r.returns[0].cpu().numpy()
-        sm = f.r.smoothness[0].cpu().numpy()
+        # read the results back on the flight's own stream: the current stream may already be running the next
+        # generation's population rollout, and a copy queued there would wait for it
+        with (torch.cuda.stream(f.stream) if f.stream is not None else _null()):
+            f.r.check()
+            steps = f.r.steps[0].cpu().numpy()
+            returns = f.r.returns[0].cpu().numpy()
+            sm = f.r.smoothness[0].cpu().numpy()
+            hist = {}
+            if f.r.trace is not None and (want_history or f.n == 1):
+                hist = {e: f.r.trace[0, e, :int(steps[e])].cpu().numpy() for e in range(f.n)}
+            elif want_history:
+                hist = {e: f.r.actions[0, e, :int(steps[e])].cpu().numpy().astype(np.float64) for e in range(f.n)}
         if f.noise_state is not None:
             np.random.set_state(f.noise_state)
             np.random.randn(int(steps[0]), 3)
         if store_transition:
+            if f.stream is not None:
+                f.r.replay.record_stream(torch.cuda.current_stream(self.device))     # read below by kernels of this stream
             self._store_rows(agent, f.r.replay[0], int(steps[0]))
         env = self.env
         theta_trim = np.rad2deg(self._initial_state(env)[7])
@@ -165,12 +187,12 @@ class Agent:
             fitness = float(returns[e]) + (float(sm[e]) if self.args.smooth_fitness else 0.0)
             state_lst, actions, rewards = [], None, None
             if f.r.trace is not None and (want_history or f.n == 1):
-                tr = f.r.trace[0, e, :n].cpu().numpy()
+                tr = hist[e]
                 rewards = [float(x) for x in tr[:, 15]]
                 actions = tr[:, 12:15].copy()
                 state_lst = [] if store_transition else [tr[k, 0:12].copy() for k in range(n)]
             else:
-                actions = f.r.actions[0, e, :n].cpu().numpy().astype(np.float64) if want_history else np.zeros((0, 3))
+                actions = hist[e] if want_history else np.zeros((0, 3))
                 rewards = _ReturnOnly(float(returns[e]))
             eps.append(Episode(fitness=fitness, smoothness=float(sm[e]), length=self._final_time(n), state_history=state_lst,
                                ref_signals=refs, actions=actions, reward_lst=rewards))
@@ -240,6 +262,11 @@ class Agent:
         """agent.py:229-245 as one fused launch: every actor x num_envs references.  Returns (pop_fitness f64[pop] numpy,
         device fitness, per-actor record matrix numpy [fitness, sum len, sum len^2, stored frames, sum sm, sum sm^2, has sm])
         — identical on every rank."""
+        return self._finish_population(self._launch_population(sm_limit))
+
+    def _launch_population(self, sm_limit=0):
+        """the asynchronous half: reference draws, K0 + K1 (+ K6) and the per-actor record of this rank's shard, all queued
+        on the current stream; nothing here waits for the device and nothing is stored yet."""
         n_envs = int(getattr(self.args, 'num_envs', self.args.num_evals))
         draws = [self.env.draw_reference() for _ in range(n_envs)]
         lv = _to_device(np.stack([d[0] for d in draws]), self.device)
@@ -271,6 +298,15 @@ class Agent:
                 rec[:, 4] = sm_all.sum(1)
                 rec[:, 5] = (sm_all ** 2).sum(1)
                 rec[:, 6] = 1.0
+        return (r, rec, (lv, st, md))
+
+    def _finish_population(self, launched):
+        """the collecting half: all-gather of the record (and of the stored transitions), buffers, counters."""
+        r, rec, _inputs = launched
+        store = self.store_population_transitions
+        world, rank = engine.world_info()
+        pop = len(self.pop)
+        horizon = self._horizon()
         rec_all = engine.gather_rows(rec, pop, world, rank)
         self._last_result = r
         if store:
@@ -292,6 +328,40 @@ class Agent:
         self.num_episodes += pop
         return rec_host[:, 0].copy(), rec_all[:, 0].contiguous(), rec_host
 
+    # A generation's FRONT: everything that can be queued before any of its results is needed.
+    def _signature(self):
+        """what the front of a generation read: a front launched ahead of time is only used if none of it changed."""
+        env = self.env
+        return (self.pop.genomes._version if len(self.pop) else 0,
+                tuple(p._version for p in self.rl_agent.actor.parameters()),
+                id(env), env.mode_code, float(env.t_max), int(getattr(self.args, 'num_envs', self.args.num_evals)), len(self.pop))
+
+    def _launch_front(self):
+        args = self.args
+        fr = _Front()
+        fr.signature = self._signature()
+        log = bool(args.should_log)
+        # RL exploration episode (agent.py:267-268): independent of the population -> side stream, launched first.  The RL
+        # validation (:273-275) reads the RL actor AFTER train_rl; when no gradient step can happen it joins the side stream.
+        fr.f_explore = self._fly(self.rl_agent, 1, is_action_noise=True, store_transition=True, trace=log, stream=self._side)
+        fr.f_rlval = self._fly(self.rl_agent, self.validation_tests, trace=log, stream=self._side2) if args.frac_frames_train == 0 else None
+        fr.spec, fr.val_draws, fr.pop = {}, None, None
+        if len(self.pop):
+            # Speculative champion validation: the champion is only known after the ranking, and its 5 validation episodes
+            # are ~0.15 s of serial latency.  The ranked elites of the previous generation survive unchanged (and so do
+            # their protected clones), and one of the best of them usually wins again: their validation episodes are
+            # launched NOW, next to the population rollout; a miss falls back to the serial launch.
+            fr.val_draws = [self.env.draw_reference() for _ in range(self.validation_tests)]
+            plan = getattr(self.evolver, 'last_plan', None)
+            if plan is not None and self.speculative_validations > 0:
+                for j, (o, c) in enumerate(list(zip(plan.elitist_index, plan.new_elitists))[:self.speculative_validations]):
+                    fr.spec[o] = fr.spec[c] = self._fly(self.pop[o], self.validation_tests, trace=log,
+                                                        stream=self._spec_streams[j], draws=fr.val_draws)
+            # leave one SM per flight that can be in the air next to the rollout: exploration, RL validation, the previous
+            # generation's champion validation, speculative validations
+            fr.pop = self._launch_population(sm_limit=-(3 + len(fr.spec) // 2))
+        return fr
+
     def train(self):
         self.iterations += 1
         self.gen_frames = 0
@@ -300,8 +370,6 @@ class Agent:
         ep_len_avg = ep_len_sd = 0.
         pop_fitness = None
         args = self.args
-        # RL exploration episode (agent.py:267-268): independent of the population -> side stream, launched first.  The RL
-        # validation (:273-275) reads the RL actor AFTER train_rl; when no gradient step can happen it joins the side stream.
         import time as _time
         tm = self.timing = {}
         t_prev = [_time.perf_counter()]
@@ -310,26 +378,17 @@ class Agent:
             now = _time.perf_counter()
             tm[name] = tm.get(name, 0.0) + 1e3 * (now - t_prev[0])
             t_prev[0] = now
-        early_validation = args.frac_frames_train == 0
-        f_explore = self._fly(self.rl_agent, 1, is_action_noise=True, store_transition=True, trace=bool(args.should_log), stream=self._side)
-        lap('launch_exploration')
-        f_rlval = self._fly(self.rl_agent, self.validation_tests, trace=bool(args.should_log), stream=self._side) if early_validation else None
-        lap('launch_rl_flights')
+        fr, self._prefetched = self._prefetched, None
+        if fr is not None and fr.signature != self._signature():
+            fr = None                  # the population / RL actor / environment changed since it was launched: fly again
+        tm['front_prefetched'] = float(fr is not None)
+        if fr is None:
+            fr = self._launch_front()
+        f_explore, f_rlval, spec, val_draws = fr.f_explore, fr.f_rlval, fr.spec, fr.val_draws
+        lap('launch_front')
         f_champ = None
         if len(self.pop):
-            # Speculative champion validation: the champion is only known after the ranking, and its 5 validation episodes
-            # are ~0.15 s of serial latency.  The ranked elites of the previous generation survive unchanged (and so do
-            # their protected clones), and one of the best of them usually wins again: their validation episodes are
-            # launched NOW, next to the population rollout; a miss falls back to the serial launch.
-            val_draws = [self.env.draw_reference() for _ in range(self.validation_tests)]
-            spec = {}
-            plan = getattr(self.evolver, 'last_plan', None)
-            if plan is not None and self.speculative_validations > 0:
-                for j, (o, c) in enumerate(list(zip(plan.elitist_index, plan.new_elitists))[:self.speculative_validations]):
-                    spec[o] = spec[c] = self._fly(self.pop[o], self.validation_tests, trace=bool(args.should_log),
-                                                  stream=self._spec_streams[j], draws=val_draws)
-            lap('launch_speculative_validation')
-            pop_fitness, dev_fitness, rec = self.evaluate_population(sm_limit=-(2 + len(spec) // 2))
+            pop_fitness, dev_fitness, rec = self._finish_population(fr.pop)
             lap('evaluate_population')
             n_envs = int(getattr(args, 'num_envs', args.num_evals))
             n_ep = len(self.pop) * n_envs
@@ -355,7 +414,7 @@ class Agent:
                 self.spec_hits += ci in spec
             f_champ = spec.get(ci)
             if f_champ is None:
-                f_champ = self._fly(self.champion, self.validation_tests, trace=bool(args.should_log), stream=self._side, copy_genome=True,
+                f_champ = self._fly(self.champion, self.validation_tests, trace=bool(args.should_log), stream=self._champ, copy_genome=True,
                                     draws=val_draws)
             lap('stats')
             elite_index = self.evolver.epoch(self.pop, dev_fitness)
@@ -366,14 +425,7 @@ class Agent:
         rl_train_scores = self.train_rl(self.gen_frames)
         lap('train_rl')
         if f_rlval is None:
-            f_rlval = self._fly(self.rl_agent, self.validation_tests, trace=bool(args.should_log))
-        rl_reward, rl_std, rl_ep_len, rl_ep_std, rl_episode, rl_sm, rl_sm_sd = self._validation_stats(
-            self._collect(self.rl_agent, f_rlval, want_history=bool(args.should_log)))
-        lap('rl_validation')
-        if args.pop_size == 0:
-            ep_len_avg, ep_len_sd = rl_ep_len, rl_ep_std
-        if args.should_log:
-            self.rl_history = rl_episode.get_history()
+            f_rlval = self._fly(self.rl_agent, self.validation_tests, trace=bool(args.should_log), stream=self._side2)
         # actor injection (agent.py:283-294)
         if args.pop_size and self.iterations % args.rl_to_ea_synch_period == 0:
             replace_index = int(np.argmin(pop_fitness))
@@ -381,6 +433,19 @@ class Agent:
                 replace_index = (replace_index + 1) % len(self.pop)
             self.rl_to_evo(self.rl_agent, self.pop[replace_index])
             self.evolver.rl_policy = replace_index
+        # Everything the NEXT generation can start without this generation's validation scores is queued now, so that the
+        # validation episodes (serial latency, side streams) run next to the next population rollout instead of next to an
+        # idle GPU.  The next train() picks the front up if population, RL actor and environment are unchanged.
+        if self.prefetch_generation:
+            self._prefetched = self._launch_front()
+            lap('launch_next_front')
+        rl_reward, rl_std, rl_ep_len, rl_ep_std, rl_episode, rl_sm, rl_sm_sd = self._validation_stats(
+            self._collect(self.rl_agent, f_rlval, want_history=bool(args.should_log)))
+        lap('rl_validation')
+        if args.pop_size == 0:
+            ep_len_avg, ep_len_sd = rl_ep_len, rl_ep_std
+        if args.should_log:
+            self.rl_history = rl_episode.get_history()
         if f_champ is not None:
             test_score, test_sd, _, _, last_episode, _, _ = self._validation_stats(
                 self._collect(self.champion, f_champ, want_history=bool(args.should_log)))

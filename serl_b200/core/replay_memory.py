@@ -234,10 +234,19 @@ class ActorBuffer:
         return self.owner.rows_of(self.index)
 
     def add_rows(self, rows):
-        n = rows.shape[0]
-        if n:
-            sel = torch.ones((1, n), dtype=torch.bool, device=self.owner.device)
-            self.owner.append(torch.tensor([self.index], device=self.owner.device), rows[None].to(self.owner.device), sel)
+        """append n chronological rows to this actor's ring.  Index arithmetic on the device only: no host<->device copy and
+        no synchronisation (this runs while validation episodes fly on other streams, and a pageable copy would wait for them)."""
+        n = int(rows.shape[0])
+        if n == 0:
+            return
+        o = self.owner
+        o._alloc()
+        rows = rows[-o.capacity:, :19].to(o.device, torch.float32)
+        m = int(rows.shape[0])
+        slot = (o.pos[self.index] + (n - m) + torch.arange(m, device=o.device)) % o.capacity
+        o.data[self.index, slot] = rows
+        o.pos[self.index] = (o.pos[self.index] + n) % o.capacity
+        o.count[self.index] += n
 
     def add_batch(self, states, actions, next_states, rewards, dones):
         cols = [np.asarray(v, dtype=np.float32).reshape(len(rewards), -1) for v in (states, actions, next_states, rewards, dones)]

@@ -35,26 +35,33 @@ __device__ __forceinline__ double plant_div_fast(double a, double b)
     const double q = a * r;
     return fma(fma(-b, q, a), r, q);
 }
-// sqrt: 20-bit rsqrt seed + two Newton steps + residual correction; zero / negative / non-finite go to the library
+// sqrt: 20-bit rsqrt seed + two Newton steps + residual correction, WITHOUT a branch: the right-hand side evaluates
+// signed square roots as sqrt(-x), sqrt(x) + select, so one argument of each pair is negative at every call, and a
+// fallback branch to the library would be taken four times per evaluation (and would cut the function into basic blocks
+// the scheduler cannot move work across).  Special cases by select: negative / NaN -> NaN (the seed already is),
+// 0 and denormals -> 0 (the seed flushes them to zero), +inf -> +inf.
 __device__ __forceinline__ double plant_sqrt_fast(double x)
 {
-    if (!(x > 1e-300 && x < 1e300)) return sqrt(x);
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
     const double hx = 0.5 * x;
     y = y * fma(-hx * y, y, 1.5);
     y = y * fma(-hx * y, y, 1.5);
     const double s = x * y;
-    return fma(fma(-s, s, x), 0.5 * y, s);
+    double r = fma(fma(-s, s, x), 0.5 * y, s);
+    r = (x >= 0.0 && x < 2.2250738585072014e-308) ? 0.0 : r;
+    r = (x == __longlong_as_double(0x7ff0000000000000ll)) ? x : r;
+    return r;
 }
-// sincos for |x| <= 8 (the plant's angles are bounded by the termination rule): two-term Cody-Waite reduction by pi/2
-// and the fdlibm kernel polynomials; larger arguments fall back to the library.
+// sincos: two-term Cody-Waite reduction by pi/2 (106 bits of pi/2: accurate to ~1 ulp far beyond the angles a flying
+// aircraft can reach; episodes end when an attitude limit trips) and the fdlibm kernel polynomials, no branch.  |x| > 2^20
+// (a diverged state; NaN likewise) returns NaN, which the rollout kernels report through the status word.
 __device__ __forceinline__ void plant_sincos_fast(double x, double* sp, double* cp)
 {
-    if (!(fabs(x) <= 8.0)) { sincos(x, sp, cp); return; }
     const double q = rint(x * 0.6366197723675814);
     double r = fma(-q, 1.5707963267948966, x);
     r = fma(-q, 6.123233995736766e-17, r);
+    r = (fabs(x) <= 1048576.0) ? r : __longlong_as_double(0x7ff8000000000000ll);
     const double z = r * r;
     double ps = 1.58969099521155010221e-10;
     ps = fma(ps, z, -2.50507602534068634195e-08);
@@ -74,6 +81,45 @@ __device__ __forceinline__ void plant_sincos_fast(double x, double* sp, double* 
     const double s1 = (n & 1) ? c : s, c1 = (n & 1) ? s : c;
     *sp = (n & 2) ? -s1 : s1;
     *cp = ((n + 1) & 2) ? -c1 : c1;
+}
+// log / exp / pow for the atmosphere model (density ~ (T / T0)^4.26; exp only above 11 km): the fdlibm kernels (e_log.c,
+// e_exp.c) without their special-case branches, divisions by plant_div_fast.  log, exp <= 1 ulp; pow = exp(b log a) carries
+// the rounding of b log a: <= (2 + |b ln a|) ulp, i.e. <= 3.5 ulp for the temperature ratios of 0 - 11 km.  a <= 0, NaN
+// or inf returns NaN (-> status word of the rollout kernels).
+__device__ __forceinline__ double plant_log_fast(double a)
+{
+    const long long ia = __double_as_longlong(a);
+    const long long top = (ia >> 32) + (0x3ff00000 - 0x3fe6a09e);           // a = 2^k * m, m in [sqrt(2)/2, sqrt(2))
+    const int k = (int)(top >> 20) - 0x3ff;
+    const long long hm = (top & 0x000fffff) + 0x3fe6a09e;
+    const double m = __longlong_as_double((hm << 32) | (ia & 0xffffffffll));
+    const double f = m - 1.0;
+    const double s = plant_div_fast(f, 2.0 + f);
+    const double z = s * s, w = z * z;
+    const double t1 = w * fma(w, fma(w, 1.531383769920937332e-01, 2.222219843214978396e-01), 3.999999999940941908e-01);
+    const double t2 = z * fma(w, fma(w, fma(w, 1.479819860511658591e-01, 1.818357216161805012e-01), 2.857142874366239149e-01),
+                              6.666666666666735130e-01);
+    const double R = t2 + t1;
+    const double hfsq = 0.5 * f * f;
+    const double dk = (double)k;
+    return dk * 6.93147180369123816490e-01 - ((hfsq - fma(s, hfsq + R, dk * 1.90821492927058770002e-10)) - f);
+}
+__device__ __forceinline__ double plant_exp_fast(double x)          // |x| < 700
+{
+    const double kd = rint(x * 1.44269504088896338700e+00);
+    const double hi = fma(-kd, 6.93147180369123816490e-01, x);
+    const double lo = kd * 1.90821492927058770002e-10;
+    const double r = hi - lo;
+    const double t = r * r;
+    const double c = r - t * fma(t, fma(t, fma(t, fma(t, 4.13813679705723846039e-08, -1.65339022054652515390e-06),
+                                               6.61375632143793436117e-05), -2.77777777770155933842e-03), 1.66666666666666019037e-01);
+    const double y = 1.0 - ((lo - plant_div_fast(r * c, 2.0 - c)) - hi);
+    return __longlong_as_double(__double_as_longlong(y) + ((long long)(int)kd << 52));
+}
+__device__ __forceinline__ double plant_pow_fast(double a, double b)
+{
+    const double y = plant_exp_fast(b * plant_log_fast(a));
+    return (a > 0.0 && a < 1e300) ? y : __longlong_as_double(0x7ff8000000000000ll);
 }
 __device__ __forceinline__ double plant_sin_fast(double x) { double s, c; plant_sincos_fast(x, &s, &c); return s; }
 __device__ __forceinline__ double plant_cos_fast(double x) { double s, c; plant_sincos_fast(x, &s, &c); return c; }
@@ -102,6 +148,7 @@ __device__ __forceinline__ double plant_cos_fast(double x) { double s, c; plant_
 #else
 #define PLANT_GEN(f) PLANT_STR(gen/f)
 #define PLANT_DIV(a, b) plant_div_fast((a), (b))
+#define PLANT_T3_DIV(a, b) plant_div_fast((a), (b))
 #define PLANT_SQRT plant_sqrt_fast
 #define PLANT_FABS fabs
 #define PLANT_SIN plant_sin_fast
@@ -110,9 +157,14 @@ __device__ __forceinline__ double plant_cos_fast(double x) { double s, c; plant_
 #endif
 #ifndef PLANT_F32
 #define PLANT_TAN tan
-#define PLANT_EXP exp
 #define PLANT_LOG10 log10
+#ifdef PLANT_EXACT
+#define PLANT_EXP exp
 #define PLANT_POW pow
+#else
+#define PLANT_EXP plant_exp_fast
+#define PLANT_POW plant_pow_fast
+#endif
 #endif
 #define PLANT_STR(x) #x
 #define PLANT_FN static __device__ __forceinline__
@@ -131,6 +183,30 @@ __device__ __forceinline__ double plant_cos_fast(double x) { double s, c; plant_
 #define PLANT_XI(i) ((i) < 8 ? (i) : ((i) == 9 ? 8 : ((i) == 12 ? 9 : (i) - 5)))
 #include PLANT_GEN(plant_ic.h)
 #include PLANT_GEN(plant_rhs_common.h)     // ONE function for every plant variant + per-variant parameter rows
+// Second instance of the same generated text for kernels that stage the tables (+ parameter rows) at the START of their
+// dynamic shared memory: tables and parameter rows are read as plant_smem_tab[...] — the compiler sees the shared address
+// space and emits LDS with 32-bit immediate-offset addressing.  Through the generic `plant_tab` pointer of the first
+// instance every one of the ~220 table reads of a right-hand side cost a 64-bit address computation (IADD3 pairs), an
+// R2UR of the base pointer and a generic LD: ~11 % of the function's instructions.
+extern __shared__ __align__(16) real plant_smem_tab[];
+__device__ __forceinline__ int plant_smem_index(const real* p)          // element index of a generic pointer into the staged blob
+{
+    return (int)((unsigned)__cvta_generic_to_shared(p) - (unsigned)__cvta_generic_to_shared(plant_smem_tab)) / (int)sizeof(real);
+}
+#undef PLANT_TAB
+#undef PLANT_PV
+#undef PLANT_PV_TABLE
+#define PLANT_TAB(name) (plant_smem_tab + PT_OFF_##name)
+#define PLANT_PV(k) plant_smem_tab[plant_smem_index(plant_pvrow) + (k)]
+#define PLANT_PV_TABLE static __device__ const real plant_pv_second_instance_unused[SERL_PLANT_COUNT][PLANT_NPV]
+#undef PLANT_RHS_COMMON_NAME
+#define PLANT_RHS_COMMON_NAME plant_rhs_common_smem
+#include PLANT_GEN(plant_rhs_common.h)
+#undef PLANT_RHS_COMMON_NAME
+#undef PLANT_TAB
+#undef PLANT_PV
+#define PLANT_TAB(name) (plant_tab + PT_OFF_##name)
+#define PLANT_PV(k) plant_pvrow[k]
 #undef PLANT_XI
 #define PLANT_XI(i) (i)                    // trace-only navigation states: full rtX indexing
 #include PLANT_GEN(plant_rhs_nav.h)
@@ -201,6 +277,8 @@ static __device__ __noinline__ void plant_step_nav(double* Xnav, const double* X
 // pv_post / call: time-triggered builds (cg_timed): the parameter row switches to pv_post when the model clock
 // call * 0.01 + c_s * 0.01 of a stage reaches 20 s: every stage from call SERL_TRIGGER_CALLS on, and the LAST stage (c = 1) of
 // call SERL_TRIGGER_CALLS - 1, whose time 19.99 + 0.01 already compares >= 20 in the binary.
+// STAB: tables + parameter rows staged at the start of dynamic shared memory (see plant_rhs_common_smem)
+template <bool STAB = false>
 static __device__ __noinline__ void plant_step(const real* pv, double* X, const double* U, const real* tab, bool nav = false,
                                                const real* pv_post = nullptr, int call = 0)
 {
@@ -215,7 +293,8 @@ static __device__ __noinline__ void plant_step(const real* pv, double* X, const 
 #pragma unroll
     for (int s = 0; s < 6; ++s) {
         const bool post = pv_post != nullptr && (call >= SERL_TRIGGER_CALLS || (s == 5 && call == SERL_TRIGGER_CALLS - 1));
-        plant_rhs_common(x, u, f[s], tab, post ? pv_post : pv);
+        if (STAB) plant_rhs_common_smem(x, u, f[s], tab, post ? pv_post : pv);
+        else plant_rhs_common(x, u, f[s], tab, post ? pv_post : pv);
 #pragma unroll
         for (int li = 0; li < NLIVE; ++li) {
             double acc = (double)f[0][li] * (h * B[s][0]);
@@ -344,6 +423,7 @@ __device__ __forceinline__ void sensor_noise(const RolloutArgs& a, size_t traj, 
 }
 
 // reset(): initialize(), one zero-command step returns the initial state (phlabenv.py:401-428). obs = [0,0,0,p,q,r,alpha]
+template <bool STAB = false>
 static __device__ void env_reset(Env& e, const RolloutArgs& a, int env, float* obs, size_t traj = 0)
 {
     const double* ic = plant_ic(a.env_mode[env] & 0xff);
@@ -357,11 +437,12 @@ static __device__ void env_reset(Env& e, const RolloutArgs& a, int env, float* o
     obs[3] = (float)x0[0]; obs[4] = (float)x0[1]; obs[5] = (float)x0[2]; obs[6] = (float)x0[4];
     double U[3] = {0.0, 0.0, 0.0}, cmd[3];
     apply_fault(e.fault, U, cmd);
-    plant_step(e.pv, e.X, cmd, e.tab, a.trace != nullptr, e.pv_post, 0);
+    plant_step<STAB>(e.pv, e.X, cmd, e.tab, a.trace != nullptr, e.pv_post, 0);
     e.t = 0.0; e.ret = 0.0; e.k = 0; e.done = false;
 }
 
 // one CitationEnv.step (phlabenv.py:430-482) + the bookkeeping of Agent.evaluate (agent.py:85-118)
+template <bool STAB = false>
 static __device__ void env_step(Env& e, const RolloutArgs& ar, size_t traj, int actor, bool replay, const float* a, float* obs)
 {
     const double bound = 10.0 * DEG2RAD;                       // phlabenv.py:208
@@ -393,7 +474,7 @@ static __device__ void env_step(Env& e, const RolloutArgs& ar, size_t traj, int 
     double xo[12];
 #pragma unroll
     for (int i = 0; i < 12; ++i) xo[i] = e.X[i];
-    plant_step(e.pv, e.X, cmd, e.tab, ar.trace != nullptr, e.pv_post, e.k + 1);
+    plant_step<STAB>(e.pv, e.X, cmd, e.tab, ar.trace != nullptr, e.pv_post, e.k + 1);
     sensor_noise(ar, traj, e.k + 1, xo);
 
     const double t = e.t;

@@ -42,20 +42,25 @@ PLANT_FN int plant_index(const real* x, int n, real u)
     }
 }
 
+/* interval of the table3 S-function: the first breakpoint not below u, minus one, clamped to [0, n-2].  Breakpoints are
+ * strictly increasing, so "scan while x[i] < u" stops after exactly count(x[i] < u) steps: written as that count, the search
+ * has no data-dependent loop (n is a literal at every call, the sum unrolls into compare + add). */
 PLANT_FN int plant_t3_interval(const real* x, int n, real u)
 {
-    int i = 0;
-    while (i < n && x[i] < u) ++i;
-    --i;
+    int i = -1;
+    for (int j = 0; j < n; ++j) i += (x[j] < u) ? 1 : 0;
     if (i < 0) i = 0;
     if (i > n - 2) i = n - 2;
     return i;
 }
 
+#ifndef PLANT_T3_DIV
+#define PLANT_T3_DIV(a, b) ((a) / (b))
+#endif
 PLANT_FN real plant_t3_lerp(real v0, real v1, real u, real xlo, real xhi)
 {
-    if (u == xhi) return v1;
-    return (v1 - v0) * (u - xlo) / (xhi - xlo) + v0;
+    const real y = PLANT_T3_DIV((v1 - v0) * (u - xlo), (xhi - xlo)) + v0;
+    return (u == xhi) ? v1 : y;
 }
 
 PLANT_FN real plant_table3(const real* P1, int n1, const real* P2, int n2, const real* P3, int n3,

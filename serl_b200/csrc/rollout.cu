@@ -314,10 +314,11 @@ rollout_kernel_persist(RolloutArgs ar)
 
     // this slot's share of the (task, step) space
     const long long NT = ar.n_tasks, NS = ar.n_slots;
-    long long t_first, t_last;
+    long long t_first = 0, t_last = 0;
     int k0 = 0, k1 = 0;
+    int stage = 0;                                     // 3 = no (more) segments
     if (NT <= NS) {
-        if (slot >= NT) return;
+        if (slot >= NT) stage = 3;                     // idle slot: still takes part in the CTA barriers below
         t_first = slot; t_last = slot + 1;
     } else {
         const long long W = NT * horizon;
@@ -327,101 +328,135 @@ rollout_kernel_persist(RolloutArgs ar)
     }
     // segments in the order: head of the last task (published) -> whole tasks -> tail of the first task (continued)
     long long t_cur = t_first + (k0 > 0 ? 1 : 0);
-    int stage = 0;
+    // LOCKSTEP: all warps of the CTA take their steps together (one CTA barrier per step).  The step body is ~180 KB of
+    // straight-line code (actor 100 KB, right-hand side 41 KB x 6 calls, integrator, environment); eight warps drifting
+    // through it independently each stream it through the instruction caches on their own, and instruction fetch was the
+    // top stall (no_instruction 27 % of the warp samples).  In lockstep a fetched line serves every warp of the SM.
+    Env e;
+    e.tab = tab;
+    e.done = true; e.k = 0;
+    float obs[7], a[3];
+    bool in_seg = false, pending = false, to_h = false, valid = false, replay = false;
+    int ke = 0, actor = 0;
+    size_t traj = 0;
     for (;;) {
-        long long task;
-        int kb, ke;
-        bool from_h = false, to_h = false;
-        if (stage == 0) {
-            stage = 1;
-            if (k1 == 0) continue;
-            task = t_last; kb = 0; ke = k1; to_h = true;
-        } else if (stage == 1) {
-            if (t_cur >= t_last) { stage = 2; continue; }
-            task = t_cur++; kb = 0; ke = horizon;
-        } else if (stage == 2) {
-            stage = 3;
-            if (k0 == 0) continue;
-            task = t_first; kb = k0; ke = horizon; from_h = true;
-        } else break;
-        (void)kb;
-
-        const int actor = (int)(task / ar.n_chunks), chunk = (int)(task - (long long)actor * ar.n_chunks);
-        if (actor != cur_actor) {
-            // swap the genome of this slot: everyone has left the previous segment -> one thread launches the bulk copy
-            asm volatile("bar.sync %0, %1;" ::"r"(1 + slot_l), "r"(slot_threads) : "memory");
-            if (wslot == 0 && lane == 0) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads of w before the async write
-                const uint32_t bytes = (uint32_t)ar.P4 * 4u;
-                mbar_expect_tx(&gbar[slot_l], bytes);
-                tma_bulk_g2s(w, ar.wt + (size_t)actor * ar.P4, bytes, &gbar[slot_l]);
-            }
-            mbar_wait(&gbar[slot_l], gphase);
-            gphase ^= 1;
-            cur_actor = actor;
+        // is this slot's segment still flying?  (slot-uniform: OR over the slot's warps at its named barrier)
+        bool slot_alive = false;
+        if (in_seg) {
+            int any;
+            asm volatile("{ .reg .pred p, q; setp.ne.s32 p, %1, 0; barrier.cta.red.or.pred q, %2, %3, p; selp.s32 %0, 1, 0, q; }"
+                         : "=r"(any) : "r"((int)(!e.done && e.k < ke)), "r"(1 + slot_l), "r"(slot_threads) : "memory");
+            slot_alive = any != 0;
         }
-        const int eslot = chunk * slot_threads + wslot * 32 + lane;
-        const bool valid = eslot < ar.n_envs;
-        const int env = valid ? (ar.env_order ? ar.env_order[eslot] : eslot) : 0;
-        Env e;
-        e.tab = tab;
-        float obs[7], a[3];
-        if (from_h) {      // the previous slot published this warp's trajectories when it STARTED; normally long done
-            if (lane == 0) {
-                const volatile int* f = ar.ho.flag + (slot - 1) * wps + wslot;
-                while (*f == 0) __nanosleep(200);
+        if (!slot_alive) {
+            if (in_seg) {                              // close the finished segment
+                if (to_h) {
+                    const long long hx = slot * slot_threads + wslot * 32 + lane;
+                    if (valid) {
+#pragma unroll
+                        for (int i = 0; i < NX; ++i) __stcg(ar.ho.X + (size_t)i * ar.ho.n + hx, e.X[i]);
+                        __stcg(ar.ho.t + hx, e.t); __stcg(ar.ho.ret + hx, e.ret);
+#pragma unroll
+                        for (int i = 0; i < 7; ++i) __stcg(ar.ho.obs + (size_t)i * ar.ho.n + hx, obs[i]);
+                        __stcg(ar.ho.k + hx, e.k | ((e.done ? 1 : 0) << 30));
+                    }
+                    __threadfence();
+                    __syncwarp();
+                    if (lane == 0) atomicExch(ar.ho.flag + slot * wps + wslot, 1);
+                } else if (valid) {
+                    ar.returns[traj] = e.ret;
+                    ar.steps[traj] = e.k;
+                    if (ar.status && !isfinite(e.ret + e.X[3] + e.X[7] + e.X[9])) atomicOr(ar.status, SERL_STATUS_NONFINITE);   // NaN actions poison the state at once
+                }
+                in_seg = false;
             }
-            __syncwarp();
-            __threadfence();
-        }
-        if (valid) {
-            env_bind(e, ar, env, pv_base, (size_t)actor * ar.n_envs + env);
-            if (from_h) {
-                const long long hx = (slot - 1) * slot_threads + wslot * 32 + lane;
-#pragma unroll
-                for (int i = 0; i < NX; ++i) e.X[i] = __ldcg(ar.ho.X + (size_t)i * ar.ho.n + hx);
-                e.t = __ldcg(ar.ho.t + hx); e.ret = __ldcg(ar.ho.ret + hx);
-#pragma unroll
-                for (int i = 0; i < 7; ++i) obs[i] = __ldcg(ar.ho.obs + (size_t)i * ar.ho.n + hx);
-                const int kk = __ldcg(ar.ho.k + hx);
-                e.k = kk & 0x3fffffff; e.done = ((kk >> 30) & 1) != 0;
-            } else {
-                env_reset(e, ar, env, obs, (size_t)actor * ar.n_envs + env);
+            // open the next one, if any.  The tail segment continues trajectories the PREVIOUS slot publishes at the end of
+            // its head segment: normally long done, but that slot may sit in this very CTA and advance only with this
+            // one's steps (lockstep), so the slot never blocks on the record — it stays `pending` and asks again at the next
+            // step.  All decisions are slot-uniform (AND over the slot's warps at its named barrier).
+            long long task = 0;
+            bool have = false;
+            if (!pending) {
+                to_h = false;
+                while (!have && stage < 3) {
+                    if (stage == 0) {
+                        stage = 1;
+                        if (k1 != 0) { task = t_last; ke = k1; to_h = true; have = true; }
+                    } else if (stage == 1) {
+                        if (t_cur >= t_last) stage = 2;
+                        else { task = t_cur++; ke = horizon; have = true; }
+                    } else {
+                        stage = 3;
+                        if (k0 != 0) { ke = horizon; pending = true; }
+                    }
+                }
             }
-        } else {
-            e.done = true; e.k = 0; e.ret = 0.0; e.t = 0.0; e.fault = 0; e.pv = pv_base; e.pv_post = nullptr; e.theta_trim = 0.0;
-            e.ref_lv = ar.ref_levels; e.ref_st = ar.ref_starts;
+            const bool from_h = pending;
+            if (pending) {
+                int ok = 0;
+                if (lane == 0) ok = *(const volatile int*)(ar.ho.flag + (slot - 1) * wps + wslot) != 0;
+                ok = __shfl_sync(0xffffffffu, ok, 0);
+                int all;
+                asm volatile("{ .reg .pred p, q; setp.ne.s32 p, %1, 0; barrier.cta.red.and.pred q, %2, %3, p; selp.s32 %0, 1, 0, q; }"
+                             : "=r"(all) : "r"(ok), "r"(1 + slot_l), "r"(slot_threads) : "memory");
+                if (all) { pending = false; task = t_first; have = true; __threadfence(); }
+                else __nanosleep(500);
+            }
+            if (have) {
+                actor = (int)(task / ar.n_chunks);
+                const int chunk = (int)(task - (long long)actor * ar.n_chunks);
+                if (actor != cur_actor) {
+                    // swap the genome of this slot: everyone has left the previous segment -> one thread launches the bulk copy
+                    asm volatile("bar.sync %0, %1;" ::"r"(1 + slot_l), "r"(slot_threads) : "memory");
+                    if (wslot == 0 && lane == 0) {
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads of w before the async write
+                        const uint32_t bytes = (uint32_t)ar.P4 * 4u;
+                        mbar_expect_tx(&gbar[slot_l], bytes);
+                        tma_bulk_g2s(w, ar.wt + (size_t)actor * ar.P4, bytes, &gbar[slot_l]);
+                    }
+                    mbar_wait(&gbar[slot_l], gphase);
+                    gphase ^= 1;
+                    cur_actor = actor;
+                }
+                const int eslot = chunk * slot_threads + wslot * 32 + lane;
+                valid = eslot < ar.n_envs;
+                const int env = valid ? (ar.env_order ? ar.env_order[eslot] : eslot) : 0;
+                traj = (size_t)actor * ar.n_envs + env;
+                if (valid) {
+                    env_bind(e, ar, env, pv_base, traj);
+                    if (from_h) {
+                        const long long hx = (slot - 1) * slot_threads + wslot * 32 + lane;
 #pragma unroll
-            for (int i = 0; i < NX; ++i) e.X[i] = 0.0;
+                        for (int i = 0; i < NX; ++i) e.X[i] = __ldcg(ar.ho.X + (size_t)i * ar.ho.n + hx);
+                        e.t = __ldcg(ar.ho.t + hx); e.ret = __ldcg(ar.ho.ret + hx);
 #pragma unroll
-            for (int i = 0; i < 7; ++i) obs[i] = 0.f;
+                        for (int i = 0; i < 7; ++i) obs[i] = __ldcg(ar.ho.obs + (size_t)i * ar.ho.n + hx);
+                        const int kk = __ldcg(ar.ho.k + hx);
+                        e.k = kk & 0x3fffffff; e.done = ((kk >> 30) & 1) != 0;
+                    } else {
+                        env_reset<TABS>(e, ar, env, obs, traj);
+                    }
+                } else {
+                    e.done = true; e.k = 0; e.ret = 0.0; e.t = 0.0; e.fault = 0; e.pv = pv_base; e.pv_post = nullptr; e.theta_trim = 0.0;
+                    e.ref_lv = ar.ref_levels; e.ref_st = ar.ref_starts;
+#pragma unroll
+                    for (int i = 0; i < NX; ++i) e.X[i] = 0.0;
+#pragma unroll
+                    for (int i = 0; i < 7; ++i) obs[i] = 0.f;
+                }
+                replay = valid && ar.replay != nullptr && env == ar.replay_env;
+                in_seg = true;
+            }
         }
-        const size_t traj = (size_t)actor * ar.n_envs + env;
-        const bool replay = valid && ar.replay != nullptr && env == ar.replay_env;
-        while (__any_sync(0xffffffffu, !e.done && e.k < ke)) {
+        // the CTA's warps meet here once per step; the launch ends when no slot has a segment left
+        if (!__syncthreads_or(in_seg || pending)) break;
+        const bool mine = in_seg && !e.done && e.k < ke;
+        if (__any_sync(0xffffffffu, mine)) {
             // one instantiation per activation: the choice is compiled into the 4 x h/4 activation calls of every layer
             if (actfn == SERL_ACT_TANH) actor_forward_warp<H, SERL_ACT_TANH>(w, L, lane, obs, a);
             else if (actfn == SERL_ACT_ELU) actor_forward_warp<H, SERL_ACT_ELU>(w, L, lane, obs, a);
             else actor_forward_warp<H, SERL_ACT_LEAKY_RELU>(w, L, lane, obs, a);
-            if (!e.done && e.k < ke) env_step(e, ar, traj, actor, replay, a, obs);
-        }
-        if (to_h) {
-            const long long hx = slot * slot_threads + wslot * 32 + lane;
-            if (valid) {
-#pragma unroll
-                for (int i = 0; i < NX; ++i) __stcg(ar.ho.X + (size_t)i * ar.ho.n + hx, e.X[i]);
-                __stcg(ar.ho.t + hx, e.t); __stcg(ar.ho.ret + hx, e.ret);
-#pragma unroll
-                for (int i = 0; i < 7; ++i) __stcg(ar.ho.obs + (size_t)i * ar.ho.n + hx, obs[i]);
-                __stcg(ar.ho.k + hx, e.k | ((e.done ? 1 : 0) << 30));
-            }
-            __threadfence();
-            __syncwarp();
-            if (lane == 0) atomicExch(ar.ho.flag + slot * wps + wslot, 1);
-        } else if (valid) {
-            ar.returns[traj] = e.ret;
-            ar.steps[traj] = e.k;
-            if (ar.status && !isfinite(e.ret + e.X[3] + e.X[7] + e.X[9])) atomicOr(ar.status, SERL_STATUS_NONFINITE);   // NaN actions poison the state at once
+            if (mine) env_step<TABS>(e, ar, traj, actor, replay, a, obs);
         }
     }
 }

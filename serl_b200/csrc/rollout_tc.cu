@@ -418,7 +418,7 @@ rollout_kernel_tc(TcArgs ar)
         float obs[7], a[3];
         if (valid) {
             env_bind(e, r, env, pv_base, (size_t)actor * r.n_envs + env);
-            env_reset(e, r, env, obs, (size_t)actor * r.n_envs + env);
+            env_reset<true>(e, r, env, obs, (size_t)actor * r.n_envs + env);
         } else {
             e.done = true; e.k = 0; e.ret = 0.0; e.t = 0.0; e.fault = 0; e.pv = pv_base; e.pv_post = nullptr; e.theta_trim = 0.0;
             e.ref_lv = r.ref_levels; e.ref_st = r.ref_starts;
@@ -431,7 +431,7 @@ rollout_kernel_tc(TcArgs ar)
         const bool replay = valid && r.replay != nullptr && env == r.replay_env;
         while (group_any(c.grp, !e.done)) {
             tc_actor_forward<ACT>(c, ar, tiles_actor, obs, a);
-            if (!e.done) env_step(e, r, traj, actor, replay, a, obs);
+            if (!e.done) env_step<true>(e, r, traj, actor, replay, a, obs);
         }
         if (valid) {
             r.returns[traj] = e.ret;

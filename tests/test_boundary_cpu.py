@@ -137,3 +137,32 @@ def test_calc_smoothness_matches_reference_formula_literal():
             Syy[:, i] = np.abs(Y[1:N // 2] * np.conjugate(Y[1:N // 2])) * dt
         ref = -np.sqrt(np.sum(np.einsum('ij,i -> j', Syy, freq) * 2 / N)) * 100 * (80 / T)
         assert np.isclose(calc_smoothness(y), ref, rtol=1e-12, atol=0)
+
+
+def test_device_replay_rings_keep_reference_ring_semantics():
+    """DeviceReplayMemory / PopulationBuffers / ActorBuffer against the reference's list-with-position ring
+    (base/core/replay_memory.py:40-62): same content in the same chronological order, for pushes that wrap and pushes
+    longer than the capacity.  (Host logic; tensors on the CPU.)"""
+    from serl_b200.core.replay_memory import ActorBuffer, DeviceReplayMemory, PopulationBuffers
+    torch.manual_seed(0)
+    for cap in (5, 8):
+        ref = []                                                 # the reference ring as a plain list
+        pos = 0
+        dev = DeviceReplayMemory(cap, 'cpu')
+        pa, pb = PopulationBuffers(3, cap, 'cpu'), PopulationBuffers(3, cap, 'cpu')
+        for n in (3, 4, 9, 1, 12, 2):
+            rows = torch.randn(n, 20)
+            for r in rows:                                       # replay_memory.py:53-62 push()
+                if len(ref) < cap:
+                    ref.append(None)
+                ref[pos] = r[:19]
+                pos = (pos + 1) % cap
+            dev.add_rows(rows)
+            ActorBuffer(pa, 1).add_rows(rows)
+            pb.append(torch.tensor([1]), rows[None], torch.ones((1, n), dtype=torch.bool))
+            chrono = torch.stack(ref[pos:] + ref[:pos]) if len(ref) == cap else torch.stack(ref)
+            assert torch.equal(dev._chronological_rows(), chrono)
+            assert torch.equal(pa.rows_of(1), chrono) and torch.equal(pb.rows_of(1), chrono)
+            assert torch.equal(pa.data, pb.data) and torch.equal(pa.pos, pb.pos) and torch.equal(pa.count, pb.count)
+            assert len(dev) == len(ActorBuffer(pa, 1)) == len(ref)
+        assert len(ActorBuffer(pa, 0)) == 0 and pa.rows_of(2).shape == (0, 19)

@@ -128,6 +128,45 @@ def test_agent_train_generations_and_checkpoint_format():
     assert np.array_equal(OA.flatten(oracle_actor), ag.pop.genomes[int(stats['elite_index'])].cpu().numpy())
 
 
+def _train_generations(prefetch, n, poke=None):
+    from serl_b200.core import agent as agent_mod
+    from serl_b200.envs import config
+    args = make_args(pop=6, hidden=16)
+    args.prefetch_generation = prefetch
+    env = config.select_env('PHlab_attitude_nominal')
+    torch.manual_seed(7); np.random.seed(7); random.seed(7)
+    env.seed(7)
+    ag = agent_mod.Agent(args, env)
+    out, flags = [], []
+    for g in range(n):
+        if poke is not None and g == poke:
+            ag.pop.genomes[2].mul_(0.5)          # the caller edits an actor between two generations
+        out.append(ag.train())
+        flags.append(ag.timing['front_prefetched'])
+    torch.cuda.synchronize()
+    return out, flags, ag
+
+
+def test_next_generation_front_launched_ahead_changes_no_result():
+    """train() queues the next generation's rollouts before waiting for its own validation scores; the statistics of
+    every generation, the populations and the counters must equal those of strictly one generation per call."""
+    a, fa, aga = _train_generations(True, 3)
+    b, fb, agb = _train_generations(False, 3)
+    assert fa == [0.0, 1.0, 1.0] and fb == [0.0, 0.0, 0.0]
+    for x, y in zip(a, b):
+        for k in x:
+            assert (x[k] == y[k]) or (np.isnan(x[k]) and np.isnan(y[k])), k
+    assert torch.equal(aga.pop.genomes, agb.pop.genomes)
+    assert (aga.num_frames, aga.num_episodes) == (agb.num_frames, agb.num_episodes)
+    assert len(aga.replay_buffer) == len(agb.replay_buffer)
+
+
+def test_front_launched_ahead_is_dropped_when_the_population_changed():
+    a, fa, _ = _train_generations(True, 3, poke=1)
+    assert fa == [0.0, 0.0, 1.0]
+    assert all(np.isfinite(s['best_train_fitness']) for s in a)
+
+
 def test_smoothness_kernel_matches_reference_formula():
     """K6 vs calc_smoothness (base/core/utils.py:82-120) on real action histories, incl. an early-terminated episode."""
     from serl_b200 import rollout
