@@ -355,7 +355,7 @@ def run_ours(args):
                               'BASELINE config 4: ONE population of 512 actors sharded over the GPUs, fault/plant mode per env uniform over '
                               '{nominal,be,jr,sa,se,ice,cg}, identical population on every rank'),
                  'value': m2['value'], 'unit': 'env-steps/s', 'ms_per_step': m2['elapsed_ms'] / 2, 'executed_steps_per_step': m2['total_steps'],
-                 'note': 'strong scaling is bounded by the serial latency of one 2001-step trajectory (about 0.15 s for a warp alone on an '
+                 'note': 'strong scaling is bounded by the serial latency of one 2001-step trajectory (about 0.11 s for a warp alone on an '
                          'SM): with 64 actors x 4 warps per GPU the SMs hold 2 resident warps instead of 8'}
         del wl2, m2
 
@@ -417,7 +417,7 @@ def run_ours(args):
             strict_ms, strict_stats, ag1 = agent_train_timing(dev, POP, N_ENVS, generations=3, prefetch=False)
             agent_line = {'generation_ms': ag_ms, 'population_rollout_ms': m['kern_ms'], 'ratio_to_population_rollout': ag_ms / m['kern_ms'],
                           'what': 'wall clock between successive returns of Agent.train() (EA loop, -test_ea): RL exploration, RL validation and '
-                                  'champion validation episodes (5 x 2001-step trajectories, ~0.15 s of serial latency each) fly on side streams '
+                                  'champion validation episodes (5 x 2001-step trajectories, ~0.11 s of serial latency each) fly on side streams '
                                   'and spare SMs; train() queues the next generation\'s rollouts before it waits for its own validation scores, '
                                   'so the validation latency overlaps the next population rollout',
                           'frames_per_generation': int(ag.gen_frames), 'test_score': float(ag_stats['test_score']),

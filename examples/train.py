@@ -30,6 +30,8 @@ parser.add_argument('-distil_type', type=str, default='fitness')
 parser.add_argument('-sync_period', type=int, default=1)
 parser.add_argument('-num_envs', type=int, default=3)
 parser.add_argument('-hidden_size', type=int, default=72)
+parser.add_argument('-no_prefetch', dest='prefetch_generation', default=True, action='store_false',
+                    help='strictly one generation per Agent.train() call (no rollouts of the next generation queued ahead)')
 
 if __name__ == '__main__':
     cla = parser.parse_args()

@@ -188,7 +188,14 @@ __device__ __forceinline__ double plant_cos_fast(double x) { double s, c; plant_
 // space and emits LDS with 32-bit immediate-offset addressing.  Through the generic `plant_tab` pointer of the first
 // instance every one of the ~220 table reads of a right-hand side cost a 64-bit address computation (IADD3 pairs), an
 // R2UR of the base pointer and a generic LD: ~11 % of the function's instructions.
-extern __shared__ __align__(16) real plant_smem_tab[];
+// Every kernel that uses the shared-space instance declares its dynamic shared memory with the SAME alignment as this
+// symbol (128): nvcc places each `extern __shared__` array at (end of the kernel's static shared memory) rounded up to that
+// array's own alignment, so differently aligned declarations can name different addresses (plant_tab_check() traps then).
+extern __shared__ __align__(128) real plant_smem_tab[];
+__device__ __forceinline__ void plant_tab_check(const void* dynamic_smem_base)
+{
+    if ((const void*)plant_smem_tab != dynamic_smem_base) __trap();
+}
 __device__ __forceinline__ int plant_smem_index(const real* p)          // element index of a generic pointer into the staged blob
 {
     return (int)((unsigned)__cvta_generic_to_shared(p) - (unsigned)__cvta_generic_to_shared(plant_smem_tab)) / (int)sizeof(real);

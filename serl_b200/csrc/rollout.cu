@@ -283,8 +283,9 @@ template <int H, bool TABS>
 __global__ void __launch_bounds__(MAX_CTA_THREADS, 1)
 rollout_kernel_persist(RolloutArgs ar)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];     // same alignment as plant_smem_tab (plant_env.cuh)
     __shared__ uint64_t gbar[4];                       // one mbarrier per genome slot
+    if (TABS) plant_tab_check(smem_raw);
     real* tab_s = reinterpret_cast<real*>(smem_raw);
     constexpr int TABN = PT_TOTAL + SERL_PLANT_COUNT * PLANT_NPV;      // tables + per-variant parameter rows
     constexpr int TABN2 = (TABN + 1) & ~1;
@@ -449,15 +450,19 @@ rollout_kernel_persist(RolloutArgs ar)
             }
         }
         // the CTA's warps meet here once per step; the launch ends when no slot has a segment left
+#ifdef K1_SLOT_ONLY
+        if (!(in_seg || pending)) break;        // experiment: lockstep inside a slot only (its named barrier above), slots drift
+#else
         if (!__syncthreads_or(in_seg || pending)) break;
+#endif
         const bool mine = in_seg && !e.done && e.k < ke;
         if (__any_sync(0xffffffffu, mine)) {
             // one instantiation per activation: the choice is compiled into the 4 x h/4 activation calls of every layer
             if (actfn == SERL_ACT_TANH) actor_forward_warp<H, SERL_ACT_TANH>(w, L, lane, obs, a);
             else if (actfn == SERL_ACT_ELU) actor_forward_warp<H, SERL_ACT_ELU>(w, L, lane, obs, a);
             else actor_forward_warp<H, SERL_ACT_LEAKY_RELU>(w, L, lane, obs, a);
-            if (mine) env_step<TABS>(e, ar, traj, actor, replay, a, obs);
         }
+        if (mine) env_step<TABS>(e, ar, traj, actor, replay, a, obs);
     }
 }
 
@@ -670,8 +675,8 @@ smoothness_kernel(const float* __restrict__ actions, const int* __restrict__ ste
 // N (the episode length) is arbitrary (2001 = 3*23*29 for a full episode, anything for an early termination), so the
 // length-N DFT is written as a circular convolution of size FM = 4096 >= 2N-1 with the chirp b[m] = exp(i pi m^2 / N):
 //   Y[k] = conj(b[k]) * sum_n (y[n] conj(b[n])) b[k-n]
-// = three radix-2 FFTs of size 4096 in shared memory per transform (forward DIF: natural -> bit-reversed order; the
-// pointwise product with the chirp spectrum in bit-reversed order; inverse DIT: bit-reversed -> natural), O(N log N)
+// = three radix-4 FFTs of size 4096 in shared memory per transform (forward DIF: natural -> digit-reversed order; the
+// pointwise product with the chirp spectrum in digit-reversed order; inverse DIT: digit-reversed -> natural), O(N log N)
 // instead of the O(N^2) of the direct form.  Two real channels share one complex transform (their spectra are separated by
 // conjugate symmetry), the channel means are removed first (bin 0 is not part of the metric), phases are reduced exactly
 // in integer arithmetic (m^2 mod 2N).  One CTA per trajectory.
@@ -685,38 +690,84 @@ __device__ __forceinline__ float2 chirp(int m, int N)      // exp(+i pi m^2 / N)
     sincospif((float)r / (float)N, &s, &c);
     return make_float2(c, s);
 }
-// forward FFT, decimation in frequency: natural order in, bit-reversed order out; tw[j] = exp(-2 pi i j / FM)
+// tw[j] = exp(-2 pi i j / FM) for j < FM/2; the upper half of the circle is the negated lower half
+__device__ __forceinline__ float2 twiddle(const float2* tw, int j)
+{
+    const float2 t = tw[j & (FM / 2 - 1)];
+    return (j & (FM / 2)) ? make_float2(-t.x, -t.y) : t;
+}
+// forward FFT, radix 4, decimation in frequency: natural order in, base-4 digit-reversed order out (6 passes over shared
+// memory for FM = 4^6 instead of the 12 of a radix-2 transform)
 __device__ void fft_dif(float2* z, const float2* tw, int tid, int nthr)
 {
-    for (int lh = FLOG - 1; lh >= 0; --lh) {
-        const int half = 1 << lh;
-        for (int j = tid; j < FM / 2; j += nthr) {
-            const int pos = j & (half - 1), i0 = ((j >> lh) << (lh + 1)) + pos, i1 = i0 + half;
-            const float2 a = z[i0], b = z[i1];
-            z[i0] = make_float2(a.x + b.x, a.y + b.y);
-            z[i1] = cmul(make_float2(a.x - b.x, a.y - b.y), tw[pos << (FLOG - 1 - lh)]);
+    for (int lq = FLOG - 2; lq >= 0; lq -= 2) {          // quarter span q = 2^lq, block L = 4q
+        const int q = 1 << lq, tstep = FM >> (lq + 2);
+        for (int j = tid; j < FM / 4; j += nthr) {
+            const int pos = j & (q - 1), i0 = ((j >> lq) << (lq + 2)) + pos;
+            const float2 a = z[i0], b = z[i0 + q], c = z[i0 + 2 * q], d = z[i0 + 3 * q];
+            const float2 t0 = make_float2(a.x + c.x, a.y + c.y), t1 = make_float2(a.x - c.x, a.y - c.y);
+            const float2 t2 = make_float2(b.x + d.x, b.y + d.y), t3 = make_float2(b.x - d.x, b.y - d.y);
+            // X0 = t0 + t2, X2 = t0 - t2, X1 = t1 - i t3, X3 = t1 + i t3
+            const float2 x0 = make_float2(t0.x + t2.x, t0.y + t2.y), x2 = make_float2(t0.x - t2.x, t0.y - t2.y);
+            const float2 x1 = make_float2(t1.x + t3.y, t1.y - t3.x), x3 = make_float2(t1.x - t3.y, t1.y + t3.x);
+            const int w = pos * tstep;
+            z[i0] = x0;
+            z[i0 + q] = cmul(x1, twiddle(tw, w));
+            z[i0 + 2 * q] = cmul(x2, twiddle(tw, 2 * w));
+            z[i0 + 3 * q] = cmul(x3, twiddle(tw, 3 * w));
         }
         __syncthreads();
     }
 }
-// inverse FFT (unnormalised), decimation in time: bit-reversed order in, natural order out
+// inverse FFT (unnormalised), radix 4, decimation in time: digit-reversed order in, natural order out
 __device__ void ifft_dit(float2* z, const float2* tw, int tid, int nthr)
 {
-    for (int lh = 0; lh < FLOG; ++lh) {
-        const int half = 1 << lh;
-        for (int j = tid; j < FM / 2; j += nthr) {
-            const int pos = j & (half - 1), i0 = ((j >> lh) << (lh + 1)) + pos, i1 = i0 + half;
-            const float2 t = tw[pos << (FLOG - 1 - lh)];
-            const float2 a = z[i0], b = cmul(z[i1], make_float2(t.x, -t.y));
-            z[i0] = make_float2(a.x + b.x, a.y + b.y);
-            z[i1] = make_float2(a.x - b.x, a.y - b.y);
+    for (int lq = 0; lq <= FLOG - 2; lq += 2) {
+        const int q = 1 << lq, tstep = FM >> (lq + 2);
+        for (int j = tid; j < FM / 4; j += nthr) {
+            const int pos = j & (q - 1), i0 = ((j >> lq) << (lq + 2)) + pos;
+            const int w = pos * tstep;
+            const float2 w1 = twiddle(tw, w), w2 = twiddle(tw, 2 * w), w3 = twiddle(tw, 3 * w);
+            const float2 a = z[i0], b = cmul(z[i0 + q], make_float2(w1.x, -w1.y));
+            const float2 c = cmul(z[i0 + 2 * q], make_float2(w2.x, -w2.y)), d = cmul(z[i0 + 3 * q], make_float2(w3.x, -w3.y));
+            const float2 t0 = make_float2(a.x + c.x, a.y + c.y), t1 = make_float2(a.x - c.x, a.y - c.y);
+            const float2 t2 = make_float2(b.x + d.x, b.y + d.y), t3 = make_float2(b.x - d.x, b.y - d.y);
+            // x0 = t0 + t2, x2 = t0 - t2, x1 = t1 + i t3, x3 = t1 - i t3
+            z[i0] = make_float2(t0.x + t2.x, t0.y + t2.y);
+            z[i0 + q] = make_float2(t1.x - t3.y, t1.y + t3.x);
+            z[i0 + 2 * q] = make_float2(t0.x - t2.x, t0.y - t2.y);
+            z[i0 + 3 * q] = make_float2(t1.x + t3.y, t1.y - t3.x);
         }
         __syncthreads();
     }
 }
 
+// twiddles + the chirp-filter spectrum of a FULL episode (N = horizon), once per launch: most trajectories of a trained
+// population run the whole horizon, and for them the filter transform is a fifth of the work
 __global__ void __launch_bounds__(256)
-smoothness_fft_kernel(const float* __restrict__ actions, const int* __restrict__ steps, int horizon, double dt, double* __restrict__ out)
+smoothness_prep_kernel(int horizon, float2* __restrict__ tw_g, float2* __restrict__ hf_g)
+{
+    __shared__ float2 hf[FM];
+    __shared__ float2 tw[FM / 2];
+    const int tid = threadIdx.x;
+    for (int j = tid; j < FM / 2; j += 256) {
+        float s, c;
+        sincospif(-2.0f * (float)j / (float)FM, &s, &c);
+        tw[j] = make_float2(c, s);
+    }
+    for (int m = tid; m < FM; m += 256) {
+        const int d = m < horizon ? m : (FM - m < horizon ? FM - m : -1);
+        hf[m] = d >= 0 ? chirp(d, horizon) : make_float2(0.f, 0.f);
+    }
+    __syncthreads();
+    fft_dif(hf, tw, tid, 256);
+    for (int j = tid; j < FM / 2; j += 256) tw_g[j] = tw[j];
+    for (int m = tid; m < FM; m += 256) hf_g[m] = hf[m];
+}
+
+__global__ void __launch_bounds__(256)
+smoothness_fft_kernel(const float* __restrict__ actions, const int* __restrict__ steps, int horizon, double dt, double* __restrict__ out,
+                      const float2* __restrict__ tw_g, const float2* __restrict__ hf_g)
 {
     extern __shared__ __align__(16) unsigned char sm_raw[];
     float2* z = reinterpret_cast<float2*>(sm_raw);            // [FM] work buffer
@@ -729,11 +780,7 @@ smoothness_fft_kernel(const float* __restrict__ actions, const int* __restrict__
     const int Mb = N / 2 - 1;
     if (Mb <= 0) { if (tid == 0) out[traj] = -0.0; return; }
     const float* a = actions + (size_t)traj * horizon * 3;
-    for (int j = tid; j < FM / 2; j += 256) {
-        float s, c;
-        sincospif(-2.0f * (float)j / (float)FM, &s, &c);
-        tw[j] = make_float2(c, s);
-    }
+    for (int j = tid; j < FM / 2; j += 256) tw[j] = tw_g[j];
     // channel means (bin 0 is excluded from the metric; removing it keeps the float32 transform accurate)
     double s0 = 0.0, s1 = 0.0, s2 = 0.0;
     for (int n = tid; n < N; n += 256) { s0 += a[3 * n]; s1 += a[3 * n + 1]; s2 += a[3 * n + 2]; }
@@ -744,13 +791,18 @@ smoothness_fft_kernel(const float* __restrict__ actions, const int* __restrict__
         if (tid == 0) mean_s[c] = (float)(red[0] / (double)N);
         __syncthreads();
     }
-    // chirp filter h[m] = b[|m|] for |m| < N (circular), its forward transform stays in hf
-    for (int m = tid; m < FM; m += 256) {
-        const int d = m < N ? m : (FM - m < N ? FM - m : -1);
-        hf[m] = d >= 0 ? chirp(d, N) : make_float2(0.f, 0.f);
+    // chirp filter h[m] = b[|m|] for |m| < N (circular), its forward transform stays in hf (full episodes: precomputed)
+    if (N == horizon) {
+        for (int m = tid; m < FM; m += 256) hf[m] = hf_g[m];
+        __syncthreads();
+    } else {
+        for (int m = tid; m < FM; m += 256) {
+            const int d = m < N ? m : (FM - m < N ? FM - m : -1);
+            hf[m] = d >= 0 ? chirp(d, N) : make_float2(0.f, 0.f);
+        }
+        __syncthreads();
+        fft_dif(hf, tw, tid, 256);
     }
-    __syncthreads();
-    fft_dif(hf, tw, tid, 256);
     const double fstep = Mb > 1 ? (1.0 / (2.0 * dt) - dt) / (double)(Mb - 1) : 0.0;
     const float inv_m = 1.0f / (float)FM;
     double acc = 0.0;
@@ -796,6 +848,7 @@ smoothness_fft_kernel(const float* __restrict__ actions, const int* __restrict__
     }
 }
 
+static cudaError_t scratch_get(cudaStream_t s, size_t bytes, void** out, int which);
 extern "C" int serl_smoothness(const float* d_actions, const int32_t* d_steps, int32_t n_traj, int32_t horizon, double dt,
                                double* d_out, void* stream)
 {
@@ -808,7 +861,14 @@ extern "C" int serl_smoothness(const float* d_actions, const int32_t* d_steps, i
         const size_t smem = (size_t)(2 * FM + FM / 2) * sizeof(float2);
         e = cudaFuncSetAttribute(smoothness_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return serl_fail_cuda(e, "cudaFuncSetAttribute(smoothness_fft)");
-        smoothness_fft_kernel<<<n_traj, 256, smem, (cudaStream_t)stream>>>(d_actions, d_steps, horizon, dt, d_out);
+        void* tabs = nullptr;
+        e = scratch_get((cudaStream_t)stream, (size_t)(FM + FM / 2) * sizeof(float2), &tabs, 1);
+        if (e != cudaSuccess) return serl_fail_cuda(e, "smoothness scratch");
+        float2* tw_g = (float2*)tabs;
+        float2* hf_g = tw_g + FM / 2;
+        smoothness_prep_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(horizon, tw_g, hf_g);
+        serl_count_launch();
+        smoothness_fft_kernel<<<n_traj, 256, smem, (cudaStream_t)stream>>>(d_actions, d_steps, horizon, dt, d_out, tw_g, hf_g);
         serl_count_launch();
         e = cudaGetLastError();
         return e == cudaSuccess ? SERL_OK : serl_fail_cuda(e, "smoothness_fft_kernel");
@@ -881,13 +941,13 @@ static void choose_shape(int pop, int n_envs, int apc_max, int sms, int* apc_out
 #include <mutex>
 struct ScratchBuf { void* p; size_t bytes; };
 static std::mutex g_scratch_mu;
-static std::map<std::pair<int, cudaStream_t>, ScratchBuf> g_scratch;
-static cudaError_t scratch_get(cudaStream_t s, size_t bytes, void** out)
+static std::map<std::pair<std::pair<int, int>, cudaStream_t>, ScratchBuf> g_scratch;
+static cudaError_t scratch_get(cudaStream_t s, size_t bytes, void** out, int which)      // which: 0 = K1, 1 = K6 tables
 {
     int dev = 0;
     cudaGetDevice(&dev);
     std::lock_guard<std::mutex> lk(g_scratch_mu);
-    ScratchBuf& b = g_scratch[std::make_pair(dev, s)];
+    ScratchBuf& b = g_scratch[std::make_pair(std::make_pair(dev, which), s)];
     if (b.bytes < bytes) {
         if (b.p) { cudaStreamSynchronize(s); cudaFree(b.p); b.p = nullptr; b.bytes = 0; }
         const size_t want = bytes + bytes / 4;
@@ -920,7 +980,7 @@ static cudaError_t launch_persist(RolloutArgs& ar, int apc_max, cudaStream_t s, 
     const size_t wt_bytes = (size_t)ar.pop * ar.P4 * 4;
     const long long hn = ar.n_tasks > ar.n_slots ? ar.n_slots * wps * 32 : 0;
     const size_t ho_bytes = (size_t)hn * (NX * 8 + 8 + 8 + 7 * 4 + 4) + (size_t)(hn / 32) * 4;
-    cudaError_t e = scratch_get(s, wt_bytes + ho_bytes + 512, scratch);
+    cudaError_t e = scratch_get(s, wt_bytes + ho_bytes + 512, scratch, 0);
     if (e != cudaSuccess) return e;
     unsigned char* base = (unsigned char*)*scratch;
     float* wt = (float*)base;
@@ -984,7 +1044,7 @@ static int rollout_impl(const serl_rollout_desc& d, void* stream)
     if (warp_ok) {
         // as many genome slots per CTA as shared memory holds next to the plant tables (h <= 72: two; h = 96: one);
         // h = 128 (207 KB genome) reads the tables through L1 instead
-        const size_t budget = 227 * 1024 - 64;
+        const size_t budget = 227 * 1024 - 256;       // static shared memory + alignment of the dynamic part
         const bool tabs = tab_bytes + (size_t)ar.P4 * 4 <= budget;
         int apc_max = (int)(((tabs ? budget - tab_bytes : budget)) / ((size_t)ar.P4 * 4));
         if (apc_max > 4) apc_max = 4;

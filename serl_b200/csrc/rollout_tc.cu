@@ -399,6 +399,7 @@ rollout_kernel_tc(TcArgs ar)
     __shared__ uint32_t tmem_slot;
     __shared__ uint32_t shared_state[4];
     TcCtx c;
+    plant_tab_check(smem_raw);
     tc_setup(c, ar, smem_raw, bars, &tmem_slot, shared_state);
     const RolloutArgs& r = ar.r;
     const real* tab = reinterpret_cast<const real*>(smem_raw);

@@ -68,6 +68,8 @@ class Parameters:
             self._verbose_crossover = g('verbose_crossover', False)
         # engine knobs
         self.num_envs = g('num_envs', getattr(self, 'num_evals', 3))
+        # Agent.train() queues the next generation's rollouts before it waits for its own validation scores (core/agent.py)
+        self.prefetch_generation = bool(g('prefetch_generation', True))
         self.state_dim = None
         self.action_dim = None
         self.save_foldername = './tmp/'
