@@ -470,7 +470,7 @@ rollout_kernel_persist(RolloutArgs ar)
 __global__ void __launch_bounds__(128)
 rollout_kernel_simple(RolloutArgs ar)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     float* w = reinterpret_cast<float*>(smem_raw);
     const int P4 = (ar.P + 3) & ~3;
     float* bufA = w + P4;
@@ -504,7 +504,7 @@ __global__ void __launch_bounds__(128)
 actor_forward_kernel(const float* __restrict__ genome, int P, serl_actor_shape sh, const float* __restrict__ obs_in, int n,
                      float* __restrict__ act_out)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     float* w = reinterpret_cast<float*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31;
     for (int i = tid; i < P; i += 128) w[genome_layout_index(i, sh.state_dim, H, sh.num_layers)] = genome[i];
@@ -525,7 +525,7 @@ __global__ void __launch_bounds__(128)
 actor_forward_kernel_simple(const float* __restrict__ genome, int P, serl_actor_shape sh, const float* __restrict__ obs_in, int n,
                             float* __restrict__ act_out)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     float* w = reinterpret_cast<float*>(smem_raw);
     float* bufA = w + ((P + 3) & ~3);
     float* bufB = bufA + sh.hidden * 128;
@@ -745,7 +745,7 @@ __device__ void ifft_dit(float2* z, const float2* tw, int tid, int nthr)
 // twiddles + the chirp-filter spectrum of a FULL episode (N = horizon), once per launch: most trajectories of a trained
 // population run the whole horizon, and for them the filter transform is a fifth of the work
 __global__ void __launch_bounds__(256)
-smoothness_prep_kernel(int horizon, float2* __restrict__ tw_g, float2* __restrict__ hf_g)
+smoothness_prep_kernel(int horizon, float2* __restrict__ tw_g, float2* __restrict__ hf_g, float2* __restrict__ cb_g)
 {
     __shared__ float2 hf[FM];
     __shared__ float2 tw[FM / 2];
@@ -763,11 +763,12 @@ smoothness_prep_kernel(int horizon, float2* __restrict__ tw_g, float2* __restric
     fft_dif(hf, tw, tid, 256);
     for (int j = tid; j < FM / 2; j += 256) tw_g[j] = tw[j];
     for (int m = tid; m < FM; m += 256) hf_g[m] = hf[m];
+    for (int m = tid; m <= horizon; m += 256) cb_g[m] = chirp(m, horizon);       // b[m], m = 0 .. N
 }
 
 __global__ void __launch_bounds__(256)
 smoothness_fft_kernel(const float* __restrict__ actions, const int* __restrict__ steps, int horizon, double dt, double* __restrict__ out,
-                      const float2* __restrict__ tw_g, const float2* __restrict__ hf_g)
+                      const float2* __restrict__ tw_g, const float2* __restrict__ hf_g, const float2* __restrict__ cb_g)
 {
     extern __shared__ __align__(16) unsigned char sm_raw[];
     float2* z = reinterpret_cast<float2*>(sm_raw);            // [FM] work buffer
@@ -805,6 +806,8 @@ smoothness_fft_kernel(const float* __restrict__ actions, const int* __restrict__
     }
     const double fstep = Mb > 1 ? (1.0 / (2.0 * dt) - dt) / (double)(Mb - 1) : 0.0;
     const float inv_m = 1.0f / (float)FM;
+    const bool full = N == horizon;              // the chirp b[m] of a full episode comes from the per-launch table
+#define K6_CHIRP(m) (full ? cb_g[m] : chirp((m), N))
     double acc = 0.0;
     for (int pass = 0; pass < 2; ++pass) {
         for (int n = tid; n < FM; n += 256) {
@@ -812,7 +815,7 @@ smoothness_fft_kernel(const float* __restrict__ actions, const int* __restrict__
             if (n < N) {
                 const float re = pass == 0 ? a[3 * n] - mean_s[0] : a[3 * n + 2] - mean_s[2];
                 const float im = pass == 0 ? a[3 * n + 1] - mean_s[1] : 0.f;
-                const float2 b = chirp(n, N);
+                const float2 b = K6_CHIRP(n);
                 v = cmul(make_float2(re, im), make_float2(b.x, -b.y));
             }
             z[n] = v;
@@ -826,7 +829,7 @@ smoothness_fft_kernel(const float* __restrict__ actions, const int* __restrict__
             const double f = dt + (double)(k - 1) * fstep;
             if (pass == 0) {
                 // T[k] = conj(b[k]) c[k] = Y0[k] + i Y1[k];  Y0 = (T[k] + conj(T[N-k])) / 2,  Y1 = (T[k] - conj(T[N-k])) / (2i)
-                const float2 bk = chirp(k, N), bn = chirp(N - k, N);
+                const float2 bk = K6_CHIRP(k), bn = K6_CHIRP(N - k);
                 float2 tk = cmul(z[k], make_float2(bk.x, -bk.y)), tn = cmul(z[N - k], make_float2(bn.x, -bn.y));
                 tk.x *= inv_m; tk.y *= inv_m; tn.x *= inv_m; tn.y *= inv_m;
                 const float y0r = 0.5f * (tk.x + tn.x), y0i = 0.5f * (tk.y - tn.y);
@@ -862,13 +865,14 @@ extern "C" int serl_smoothness(const float* d_actions, const int32_t* d_steps, i
         e = cudaFuncSetAttribute(smoothness_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return serl_fail_cuda(e, "cudaFuncSetAttribute(smoothness_fft)");
         void* tabs = nullptr;
-        e = scratch_get((cudaStream_t)stream, (size_t)(FM + FM / 2) * sizeof(float2), &tabs, 1);
+        e = scratch_get((cudaStream_t)stream, (size_t)(FM + FM / 2 + FM) * sizeof(float2), &tabs, 1);
         if (e != cudaSuccess) return serl_fail_cuda(e, "smoothness scratch");
         float2* tw_g = (float2*)tabs;
         float2* hf_g = tw_g + FM / 2;
-        smoothness_prep_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(horizon, tw_g, hf_g);
+        float2* cb_g = hf_g + FM;
+        smoothness_prep_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(horizon, tw_g, hf_g, cb_g);
         serl_count_launch();
-        smoothness_fft_kernel<<<n_traj, 256, smem, (cudaStream_t)stream>>>(d_actions, d_steps, horizon, dt, d_out, tw_g, hf_g);
+        smoothness_fft_kernel<<<n_traj, 256, smem, (cudaStream_t)stream>>>(d_actions, d_steps, horizon, dt, d_out, tw_g, hf_g, cb_g);
         serl_count_launch();
         e = cudaGetLastError();
         return e == cudaSuccess ? SERL_OK : serl_fail_cuda(e, "smoothness_fft_kernel");
