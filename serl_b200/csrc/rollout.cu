@@ -285,6 +285,7 @@ rollout_kernel_persist(RolloutArgs ar)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];     // same alignment as plant_smem_tab (plant_env.cuh)
     __shared__ uint64_t gbar[4];                       // one mbarrier per genome slot
+    __shared__ uint32_t tmem_slot;                     // base address of the CTA's tensor memory (stage derivatives)
     if (TABS) plant_tab_check(smem_raw);
     real* tab_s = reinterpret_cast<real*>(smem_raw);
     constexpr int TABN = PT_TOTAL + SERL_PLANT_COUNT * PLANT_NPV;      // tables + per-variant parameter rows
@@ -305,7 +306,18 @@ rollout_kernel_persist(RolloutArgs ar)
         for (int i = 0; i < ar.apc; ++i) mbar_init(&gbar[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    // Tensor memory for the ode5 stage derivatives (plant_env.cuh): the whole 512 columns, allocated by warp 0.  Traced
+    // launches (single episodes; the navigation integrator wants all six stages) and the float build keep local memory.
+    const bool use_tmem = sizeof(real) == 8 && ar.trace == nullptr;
+    if (use_tmem && warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = use_tmem ? *reinterpret_cast<volatile uint32_t*>(&tmem_slot) : 0u;
+    const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * PLANT_TMEM_COLS_PER_WARP);
     float* w = wbase + (size_t)slot_l * ar.P4;
     const int slot_threads = wps * 32;
     const int actfn = ar.sh.activation;
@@ -450,19 +462,23 @@ rollout_kernel_persist(RolloutArgs ar)
             }
         }
         // the CTA's warps meet here once per step; the launch ends when no slot has a segment left
-#ifdef K1_SLOT_ONLY
-        if (!(in_seg || pending)) break;        // experiment: lockstep inside a slot only (its named barrier above), slots drift
-#else
         if (!__syncthreads_or(in_seg || pending)) break;
-#endif
         const bool mine = in_seg && !e.done && e.k < ke;
         if (__any_sync(0xffffffffu, mine)) {
             // one instantiation per activation: the choice is compiled into the 4 x h/4 activation calls of every layer
             if (actfn == SERL_ACT_TANH) actor_forward_warp<H, SERL_ACT_TANH>(w, L, lane, obs, a);
             else if (actfn == SERL_ACT_ELU) actor_forward_warp<H, SERL_ACT_ELU>(w, L, lane, obs, a);
             else actor_forward_warp<H, SERL_ACT_LEAKY_RELU>(w, L, lane, obs, a);
+            // with the stage derivatives in tensor memory the plant's transfers are warp-collective: every lane steps,
+            // lanes whose trajectory is over change nothing
+            if (use_tmem) env_step<TABS, true>(e, ar, traj, actor, replay, a, obs, mine, taddr);
+            else if (mine) env_step<TABS, false>(e, ar, traj, actor, replay, a, obs);
         }
-        if (mine) env_step<TABS>(e, ar, traj, actor, replay, a, obs);
+    }
+    if (use_tmem) {                                    // every warp has left the loop (it ends at a CTA barrier)
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     }
 }
 
