@@ -192,10 +192,10 @@ def timed_region(step_fn, steps, warmup, flush, sync_all):
     return t_begin.elapsed_time(t_end), float(np.mean([a.elapsed_time(b) for a, b in ev])), res
 
 
-def agent_train_timing(dev, pop, n_envs, generations=4, prefetch=True):
+def agent_train_timing(dev, pop, n_envs, generations=6, prefetch=True):
     """Generations through the public API (Agent.train, base/core/agent.py:211-315 mirror) at the bench configuration,
-    EA loop only (-test_ea: no TD3 gradient steps; the RL exploration + validation episodes still fly).  Wall clock between
-    successive returns of train(), no device synchronisation added between the calls (a training loop has none); with
+    EA loop only (-test_ea: no TD3 gradient steps; the RL exploration + validation episodes still fly).  Median wall clock
+    between successive returns of train(), no device synchronisation added between the calls (a training loop has none); with
     prefetch=False every call is followed by a full device synchronise (strictly one generation per call)."""
     import random
     import types
@@ -227,7 +227,9 @@ def agent_train_timing(dev, pop, n_envs, generations=4, prefetch=True):
         stamps.append(time.perf_counter())
     ag.last_timing = dict(ag.timing)
     torch.cuda.synchronize()                  # the front launched for a generation nobody asks for
-    return 1e3 * (stamps[-1] - stamps[0]) / generations, stats, ag
+    gaps = [1e3 * (b - a) for a, b in zip(stamps[:-1], stamps[1:])]
+    ag.generation_gaps_ms = gaps
+    return float(np.median(gaps)), stats, ag
 
 
 def run_ours(args):
@@ -416,12 +418,12 @@ def run_ours(args):
             ag_ms, ag_stats, ag = agent_train_timing(dev, POP, N_ENVS)
             strict_ms, strict_stats, ag1 = agent_train_timing(dev, POP, N_ENVS, generations=3, prefetch=False)
             agent_line = {'generation_ms': ag_ms, 'population_rollout_ms': m['kern_ms'], 'ratio_to_population_rollout': ag_ms / m['kern_ms'],
-                          'what': 'wall clock between successive returns of Agent.train() (EA loop, -test_ea): RL exploration, RL validation and '
+                          'what': 'median wall clock between successive returns of Agent.train() (EA loop, -test_ea): RL exploration, RL validation and '
                                   'champion validation episodes (5 x 2001-step trajectories, ~0.11 s of serial latency each) fly on side streams '
                                   'and spare SMs; train() queues the next generation\'s rollouts before it waits for its own validation scores, '
                                   'so the validation latency overlaps the next population rollout',
                           'frames_per_generation': int(ag.gen_frames), 'test_score': float(ag_stats['test_score']),
-                          'phases_ms_last_generation': ag.last_timing,
+                          'generation_gaps_ms': ag.generation_gaps_ms, 'phases_ms_last_generation': ag.last_timing,
                           'one_generation_per_call': {'generation_ms': strict_ms, 'ratio_to_population_rollout': strict_ms / m['kern_ms'],
                                                       'what': 'prefetch_generation=False, device synchronised after every call; speculative '
                                                               'validation of the previous elites instead',
