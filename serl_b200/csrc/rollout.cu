@@ -691,7 +691,7 @@ smoothness_kernel(const float* __restrict__ actions, const int* __restrict__ ste
 // N (the episode length) is arbitrary (2001 = 3*23*29 for a full episode, anything for an early termination), so the
 // length-N DFT is written as a circular convolution of size FM = 4096 >= 2N-1 with the chirp b[m] = exp(i pi m^2 / N):
 //   Y[k] = conj(b[k]) * sum_n (y[n] conj(b[n])) b[k-n]
-// = three radix-4 FFTs of size 4096 in shared memory per transform (forward DIF: natural -> digit-reversed order; the
+// = three FFTs of size 4096 = 16^3 in shared memory per transform (three radix-16 passes each; forward DIF: natural -> digit-reversed order; the
 // pointwise product with the chirp spectrum in digit-reversed order; inverse DIT: digit-reversed -> natural), O(N log N)
 // instead of the O(N^2) of the direct form.  Two real channels share one complex transform (their spectra are separated by
 // conjugate symmetry), the channel means are removed first (bin 0 is not part of the metric), phases are reduced exactly
@@ -712,47 +712,76 @@ __device__ __forceinline__ float2 twiddle(const float2* tw, int j)
     const float2 t = tw[j & (FM / 2 - 1)];
     return (j & (FM / 2)) ? make_float2(-t.x, -t.y) : t;
 }
-// forward FFT, radix 4, decimation in frequency: natural order in, base-4 digit-reversed order out (6 passes over shared
-// memory for FM = 4^6 instead of the 12 of a radix-2 transform)
-__device__ void fft_dif(float2* z, const float2* tw, int tid, int nthr)
+// The work arrays are padded by one element per 16 (index i lives at ZI(i)): in the last pass a thread owns 16 CONSECUTIVE
+// elements, and without the padding all 32 lanes of a warp would hit the same banks.
+#define ZI(i) ((i) + ((i) >> 4))
+#define ZN (FM + FM / 16)
+__device__ __forceinline__ void dft4(float2 a, float2 b, float2 c, float2 d, float2& x0, float2& x1, float2& x2, float2& x3)
 {
-    for (int lq = FLOG - 2; lq >= 0; lq -= 2) {          // quarter span q = 2^lq, block L = 4q
-        const int q = 1 << lq, tstep = FM >> (lq + 2);
-        for (int j = tid; j < FM / 4; j += nthr) {
-            const int pos = j & (q - 1), i0 = ((j >> lq) << (lq + 2)) + pos;
-            const float2 a = z[i0], b = z[i0 + q], c = z[i0 + 2 * q], d = z[i0 + 3 * q];
-            const float2 t0 = make_float2(a.x + c.x, a.y + c.y), t1 = make_float2(a.x - c.x, a.y - c.y);
-            const float2 t2 = make_float2(b.x + d.x, b.y + d.y), t3 = make_float2(b.x - d.x, b.y - d.y);
-            // X0 = t0 + t2, X2 = t0 - t2, X1 = t1 - i t3, X3 = t1 + i t3
-            const float2 x0 = make_float2(t0.x + t2.x, t0.y + t2.y), x2 = make_float2(t0.x - t2.x, t0.y - t2.y);
-            const float2 x1 = make_float2(t1.x + t3.y, t1.y - t3.x), x3 = make_float2(t1.x - t3.y, t1.y + t3.x);
-            const int w = pos * tstep;
-            z[i0] = x0;
-            z[i0 + q] = cmul(x1, twiddle(tw, w));
-            z[i0 + 2 * q] = cmul(x2, twiddle(tw, 2 * w));
-            z[i0 + 3 * q] = cmul(x3, twiddle(tw, 3 * w));
+    const float2 t0 = make_float2(a.x + c.x, a.y + c.y), t1 = make_float2(a.x - c.x, a.y - c.y);
+    const float2 t2 = make_float2(b.x + d.x, b.y + d.y), t3 = make_float2(b.x - d.x, b.y - d.y);
+    x0 = make_float2(t0.x + t2.x, t0.y + t2.y); x2 = make_float2(t0.x - t2.x, t0.y - t2.y);     // X1 = t1 - i t3, X3 = t1 + i t3
+    x1 = make_float2(t1.x + t3.y, t1.y - t3.x); x3 = make_float2(t1.x - t3.y, t1.y + t3.x);
+}
+__device__ __forceinline__ void idft4(float2 a, float2 b, float2 c, float2 d, float2& x0, float2& x1, float2& x2, float2& x3)
+{
+    const float2 t0 = make_float2(a.x + c.x, a.y + c.y), t1 = make_float2(a.x - c.x, a.y - c.y);
+    const float2 t2 = make_float2(b.x + d.x, b.y + d.y), t3 = make_float2(b.x - d.x, b.y - d.y);
+    x0 = make_float2(t0.x + t2.x, t0.y + t2.y); x2 = make_float2(t0.x - t2.x, t0.y - t2.y);     // x1 = t1 + i t3, x3 = t1 - i t3
+    x1 = make_float2(t1.x - t3.y, t1.y + t3.x); x3 = make_float2(t1.x + t3.y, t1.y - t3.x);
+}
+__device__ __forceinline__ float2 cmulc(float2 a, float2 b) { return cmul(a, make_float2(b.x, -b.y)); }      // a * conj(b)
+// forward FFT, decimation in frequency, natural order in, base-4 digit-reversed order out.  FM = 16^3: THREE passes over
+// shared memory, each thread (256 of them) transforms 16 elements in registers per pass = two radix-4 stages back to back
+// (stage A: span 16q, butterflies over a; stage B: span 4q, butterflies over r; element (a, r) at base + (4a + r) q).
+__device__ void fft_dif(float2* z, const float2* tw, int tid)
+{
+#pragma unroll 1
+    for (int lq = FLOG - 4; lq >= 0; lq -= 4) {
+        const int q = 1 << lq, tA = FM >> (lq + 4), tB = FM >> (lq + 2);
+        const int pos = tid & (q - 1), base = ((tid >> lq) << (lq + 4)) + pos;
+        float2 v[4][4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            float2 x0, x1, x2, x3;
+            dft4(z[ZI(base + r * q)], z[ZI(base + (4 + r) * q)], z[ZI(base + (8 + r) * q)], z[ZI(base + (12 + r) * q)], x0, x1, x2, x3);
+            const int w = (pos + r * q) * tA;
+            v[0][r] = x0; v[1][r] = cmul(x1, twiddle(tw, w)); v[2][r] = cmul(x2, twiddle(tw, 2 * w)); v[3][r] = cmul(x3, twiddle(tw, 3 * w));
+        }
+        const int wb = pos * tB;
+        const float2 b1 = twiddle(tw, wb), b2 = twiddle(tw, 2 * wb), b3 = twiddle(tw, 3 * wb);
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            float2 x0, x1, x2, x3;
+            dft4(v[a][0], v[a][1], v[a][2], v[a][3], x0, x1, x2, x3);
+            z[ZI(base + (4 * a) * q)] = x0;
+            z[ZI(base + (4 * a + 1) * q)] = cmul(x1, b1);
+            z[ZI(base + (4 * a + 2) * q)] = cmul(x2, b2);
+            z[ZI(base + (4 * a + 3) * q)] = cmul(x3, b3);
         }
         __syncthreads();
     }
 }
-// inverse FFT (unnormalised), radix 4, decimation in time: digit-reversed order in, natural order out
-__device__ void ifft_dit(float2* z, const float2* tw, int tid, int nthr)
+// inverse FFT (unnormalised), decimation in time: digit-reversed order in, natural order out; the mirror image
+__device__ void ifft_dit(float2* z, const float2* tw, int tid)
 {
-    for (int lq = 0; lq <= FLOG - 2; lq += 2) {
-        const int q = 1 << lq, tstep = FM >> (lq + 2);
-        for (int j = tid; j < FM / 4; j += nthr) {
-            const int pos = j & (q - 1), i0 = ((j >> lq) << (lq + 2)) + pos;
-            const int w = pos * tstep;
-            const float2 w1 = twiddle(tw, w), w2 = twiddle(tw, 2 * w), w3 = twiddle(tw, 3 * w);
-            const float2 a = z[i0], b = cmul(z[i0 + q], make_float2(w1.x, -w1.y));
-            const float2 c = cmul(z[i0 + 2 * q], make_float2(w2.x, -w2.y)), d = cmul(z[i0 + 3 * q], make_float2(w3.x, -w3.y));
-            const float2 t0 = make_float2(a.x + c.x, a.y + c.y), t1 = make_float2(a.x - c.x, a.y - c.y);
-            const float2 t2 = make_float2(b.x + d.x, b.y + d.y), t3 = make_float2(b.x - d.x, b.y - d.y);
-            // x0 = t0 + t2, x2 = t0 - t2, x1 = t1 + i t3, x3 = t1 - i t3
-            z[i0] = make_float2(t0.x + t2.x, t0.y + t2.y);
-            z[i0 + q] = make_float2(t1.x - t3.y, t1.y + t3.x);
-            z[i0 + 2 * q] = make_float2(t0.x - t2.x, t0.y - t2.y);
-            z[i0 + 3 * q] = make_float2(t1.x + t3.y, t1.y - t3.x);
+#pragma unroll 1
+    for (int lq = 0; lq <= FLOG - 4; lq += 4) {
+        const int q = 1 << lq, tA = FM >> (lq + 4), tB = FM >> (lq + 2);
+        const int pos = tid & (q - 1), base = ((tid >> lq) << (lq + 4)) + pos;
+        const int wb = pos * tB;
+        const float2 b1 = twiddle(tw, wb), b2 = twiddle(tw, 2 * wb), b3 = twiddle(tw, 3 * wb);
+        float2 v[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+            idft4(z[ZI(base + (4 * a) * q)], cmulc(z[ZI(base + (4 * a + 1) * q)], b1), cmulc(z[ZI(base + (4 * a + 2) * q)], b2),
+                  cmulc(z[ZI(base + (4 * a + 3) * q)], b3), v[a][0], v[a][1], v[a][2], v[a][3]);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int w = (pos + r * q) * tA;
+            float2 x0, x1, x2, x3;
+            idft4(v[0][r], cmulc(v[1][r], twiddle(tw, w)), cmulc(v[2][r], twiddle(tw, 2 * w)), cmulc(v[3][r], twiddle(tw, 3 * w)), x0, x1, x2, x3);
+            z[ZI(base + r * q)] = x0; z[ZI(base + (4 + r) * q)] = x1; z[ZI(base + (8 + r) * q)] = x2; z[ZI(base + (12 + r) * q)] = x3;
         }
         __syncthreads();
     }
@@ -763,8 +792,9 @@ __device__ void ifft_dit(float2* z, const float2* tw, int tid, int nthr)
 __global__ void __launch_bounds__(256)
 smoothness_prep_kernel(int horizon, float2* __restrict__ tw_g, float2* __restrict__ hf_g, float2* __restrict__ cb_g)
 {
-    __shared__ float2 hf[FM];
-    __shared__ float2 tw[FM / 2];
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    float2* hf = reinterpret_cast<float2*>(sm_raw);          // [ZN]
+    float2* tw = hf + ZN;                                     // [FM/2]
     const int tid = threadIdx.x;
     for (int j = tid; j < FM / 2; j += 256) {
         float s, c;
@@ -773,12 +803,12 @@ smoothness_prep_kernel(int horizon, float2* __restrict__ tw_g, float2* __restric
     }
     for (int m = tid; m < FM; m += 256) {
         const int d = m < horizon ? m : (FM - m < horizon ? FM - m : -1);
-        hf[m] = d >= 0 ? chirp(d, horizon) : make_float2(0.f, 0.f);
+        hf[ZI(m)] = d >= 0 ? chirp(d, horizon) : make_float2(0.f, 0.f);
     }
     __syncthreads();
-    fft_dif(hf, tw, tid, 256);
+    fft_dif(hf, tw, tid);
     for (int j = tid; j < FM / 2; j += 256) tw_g[j] = tw[j];
-    for (int m = tid; m < FM; m += 256) hf_g[m] = hf[m];
+    for (int m = tid; m < FM; m += 256) hf_g[m] = hf[ZI(m)];
     for (int m = tid; m <= horizon; m += 256) cb_g[m] = chirp(m, horizon);       // b[m], m = 0 .. N
 }
 
@@ -787,9 +817,9 @@ smoothness_fft_kernel(const float* __restrict__ actions, const int* __restrict__
                       const float2* __restrict__ tw_g, const float2* __restrict__ hf_g, const float2* __restrict__ cb_g)
 {
     extern __shared__ __align__(16) unsigned char sm_raw[];
-    float2* z = reinterpret_cast<float2*>(sm_raw);            // [FM] work buffer
-    float2* hf = z + FM;                                      // [FM] spectrum of the chirp filter (bit-reversed order)
-    float2* tw = hf + FM;                                     // [FM/2] twiddles
+    float2* z = reinterpret_cast<float2*>(sm_raw);            // [ZN] work buffer (padded index ZI)
+    float2* hf = z + ZN;                                      // [ZN] spectrum of the chirp filter (digit-reversed order)
+    float2* tw = hf + ZN;                                     // [FM/2] twiddles
     __shared__ double red[256];
     __shared__ float mean_s[3];
     const int traj = blockIdx.x, tid = threadIdx.x;
@@ -810,15 +840,15 @@ smoothness_fft_kernel(const float* __restrict__ actions, const int* __restrict__
     }
     // chirp filter h[m] = b[|m|] for |m| < N (circular), its forward transform stays in hf (full episodes: precomputed)
     if (N == horizon) {
-        for (int m = tid; m < FM; m += 256) hf[m] = hf_g[m];
+        for (int m = tid; m < FM; m += 256) hf[ZI(m)] = hf_g[m];
         __syncthreads();
     } else {
         for (int m = tid; m < FM; m += 256) {
             const int d = m < N ? m : (FM - m < N ? FM - m : -1);
-            hf[m] = d >= 0 ? chirp(d, N) : make_float2(0.f, 0.f);
+            hf[ZI(m)] = d >= 0 ? chirp(d, N) : make_float2(0.f, 0.f);
         }
         __syncthreads();
-        fft_dif(hf, tw, tid, 256);
+        fft_dif(hf, tw, tid);
     }
     const double fstep = Mb > 1 ? (1.0 / (2.0 * dt) - dt) / (double)(Mb - 1) : 0.0;
     const float inv_m = 1.0f / (float)FM;
@@ -834,25 +864,25 @@ smoothness_fft_kernel(const float* __restrict__ actions, const int* __restrict__
                 const float2 b = K6_CHIRP(n);
                 v = cmul(make_float2(re, im), make_float2(b.x, -b.y));
             }
-            z[n] = v;
+            z[ZI(n)] = v;
         }
         __syncthreads();
-        fft_dif(z, tw, tid, 256);
-        for (int m = tid; m < FM; m += 256) z[m] = cmul(z[m], hf[m]);
+        fft_dif(z, tw, tid);
+        for (int m = tid; m < FM; m += 256) z[ZI(m)] = cmul(z[ZI(m)], hf[ZI(m)]);
         __syncthreads();
-        ifft_dit(z, tw, tid, 256);
+        ifft_dit(z, tw, tid);
         for (int k = 1 + tid; k <= Mb; k += 256) {
             const double f = dt + (double)(k - 1) * fstep;
             if (pass == 0) {
                 // T[k] = conj(b[k]) c[k] = Y0[k] + i Y1[k];  Y0 = (T[k] + conj(T[N-k])) / 2,  Y1 = (T[k] - conj(T[N-k])) / (2i)
                 const float2 bk = K6_CHIRP(k), bn = K6_CHIRP(N - k);
-                float2 tk = cmul(z[k], make_float2(bk.x, -bk.y)), tn = cmul(z[N - k], make_float2(bn.x, -bn.y));
+                float2 tk = cmul(z[ZI(k)], make_float2(bk.x, -bk.y)), tn = cmul(z[ZI(N - k)], make_float2(bn.x, -bn.y));
                 tk.x *= inv_m; tk.y *= inv_m; tn.x *= inv_m; tn.y *= inv_m;
                 const float y0r = 0.5f * (tk.x + tn.x), y0i = 0.5f * (tk.y - tn.y);
                 const float y1r = 0.5f * (tk.y + tn.y), y1i = 0.5f * (tn.x - tk.x);
                 acc += f * ((double)y0r * y0r + (double)y0i * y0i + (double)y1r * y1r + (double)y1i * y1i);
             } else {
-                const float cr = z[k].x * inv_m, ci = z[k].y * inv_m;
+                const float cr = z[ZI(k)].x * inv_m, ci = z[ZI(k)].y * inv_m;
                 acc += f * ((double)cr * cr + (double)ci * ci);
             }
         }
@@ -877,7 +907,9 @@ extern "C" int serl_smoothness(const float* d_actions, const int32_t* d_steps, i
     cudaError_t e;
     if (!force_direct && 2 * horizon - 1 <= FM) {
         // episodes of up to 2048 steps (training: 2001): Bluestein FFT, O(N log N)
-        const size_t smem = (size_t)(2 * FM + FM / 2) * sizeof(float2);
+        const size_t smem = (size_t)(2 * ZN + FM / 2) * sizeof(float2), smem_prep = (size_t)(ZN + FM / 2) * sizeof(float2);
+        e = cudaFuncSetAttribute(smoothness_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_prep);
+        if (e != cudaSuccess) return serl_fail_cuda(e, "cudaFuncSetAttribute(smoothness_prep)");
         e = cudaFuncSetAttribute(smoothness_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return serl_fail_cuda(e, "cudaFuncSetAttribute(smoothness_fft)");
         void* tabs = nullptr;
@@ -886,7 +918,7 @@ extern "C" int serl_smoothness(const float* d_actions, const int32_t* d_steps, i
         float2* tw_g = (float2*)tabs;
         float2* hf_g = tw_g + FM / 2;
         float2* cb_g = hf_g + FM;
-        smoothness_prep_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(horizon, tw_g, hf_g, cb_g);
+        smoothness_prep_kernel<<<1, 256, smem_prep, (cudaStream_t)stream>>>(horizon, tw_g, hf_g, cb_g);
         serl_count_launch();
         smoothness_fft_kernel<<<n_traj, 256, smem, (cudaStream_t)stream>>>(d_actions, d_steps, horizon, dt, d_out, tw_g, hf_g, cb_g);
         serl_count_launch();
