@@ -36,6 +36,13 @@ enum { SERL_PLANT_H2000_V90 = 0, SERL_PLANT_ICE = 1, SERL_PLANT_CG = 2, SERL_PLA
  * time-triggered build cg_timed: variant 6, post_variant 7); the switch happens inside the ode5 step whose last stage
  * reaches 20 s, exactly as in the reference binary */
 #define SERL_TRIGGER_CALLS 2000
+/* env_mode bit 24: the `gust` build (envs/gust, envs/phlabenv.py:165-169: "vertical gust of 15 ft/s at 20 s").  Its binary
+ * evaluates the nominal right-hand side with alpha replaced by alpha - atan(w_gust / V) in every aerodynamic term while
+ * 20 s <= t <= 23 s (stage times of the ode5 step: the last stage of native call 1999, calls 2000..2299, the first stage of
+ * call 2300); checked bit for bit against the binary on the CPU, tests/test_generated_plant.py */
+#define SERL_MODE_GUST (1 << 24)
+#define SERL_GUST_END_CALLS 2300
+#define SERL_GUST_W 0x1.249ba5e353f7dp+2      /* 4.572 m/s = 15 ft/s, the literal of the gust binary */
 enum { SERL_FAULT_NONE = 0, SERL_FAULT_BE = 1, SERL_FAULT_JR = 2, SERL_FAULT_SA = 3, SERL_FAULT_SE = 4 };
 
 #define SERL_REF_BLOCKS 6   /* reference-signal blocks per channel (oracle/refsig.py) */
@@ -108,9 +115,14 @@ int serl_rollout_eval(const float* d_weights, int32_t pop, const serl_actor_shap
  *                output — row 0 for reset()'s step, row k + 1 for env step k; order p,q,r, alpha, beta, phi, theta
  *   sm_limit     > 0: use at most that many SMs (CTAs of the persistent kernel) — leaves room for small launches that run
  *                concurrently on other streams (the RL / validation episodes of Agent.train); 0 = all SMs
+ *   flags        SERL_ROLLOUT_GUST: some env of the launch flies the gust build (SERL_MODE_GUST) — selects the kernel
+ *                instantiation with the gust schedule (the training instantiation carries no trace of it; a gust env in a launch
+ *                without the flag sets SERL_STATUS_GUST_FLAG)
  * t_max <= 0 selects the training defaults (20 s, smooth width 3 s). */
 #define SERL_REPLAY_COLS 20
-enum { SERL_STATUS_NONFINITE = 1 };   /* a trajectory's state / return became NaN or infinite */
+#define SERL_ROLLOUT_GUST 1
+enum { SERL_STATUS_NONFINITE = 1,     /* a trajectory's state / return became NaN or infinite */
+       SERL_STATUS_GUST_FLAG = 2 };   /* an env has SERL_MODE_GUST but the launch was not made with SERL_ROLLOUT_GUST */
 typedef struct {
     const float* d_weights; int32_t pop; serl_actor_shape shape;
     const double* d_ref_levels; const double* d_ref_starts; const int32_t* d_env_mode; int32_t n_envs; int32_t horizon;
@@ -123,6 +135,7 @@ typedef struct {
     int32_t sm_limit;
     const int32_t* widths; int32_t n_widths;
     const float* d_sensor_noise;
+    int32_t flags;                 /* SERL_ROLLOUT_* */
 } serl_rollout_desc;
 int serl_rollout_run(const serl_rollout_desc* desc, void* stream);
 
@@ -150,8 +163,8 @@ int serl_smoothness(const float* d_actions, const int32_t* d_steps, int32_t n_tr
  * psi, x_e, y_e are not integrated (they never feed back) and keep their initial values. */
 int serl_plant_init(double* d_X, const int32_t* d_variant, int32_t n, void* stream);
 int serl_plant_step(double* d_X, const double* d_cmd, const int32_t* d_variant, int32_t n, void* stream);
-/* the same for time-triggered builds: d_variant[i] = variant | post_variant << 16, d_call[i] = number of native step() calls the
- * model has already made since initialize() (its clock in units of 0.01 s) */
+/* the same for time-triggered builds: d_variant[i] = variant | post_variant << 16 | SERL_MODE_GUST, d_call[i] = number of native
+ * step() calls the model has already made since initialize() (its clock in units of 0.01 s) */
 int serl_plant_step_timed(double* d_X, const double* d_cmd, const int32_t* d_variant, const int32_t* d_call, int32_t n, void* stream);
 
 /* ---- neuro-evolution (base/core/mod_neuro_evo.py, classic operators) -------------------------------------

@@ -23,11 +23,14 @@ class RolloutDesc(ctypes.Structure):
                 ('t_max', ctypes.c_double), ('smooth_width', ctypes.c_double),
                 ('d_env_order', ctypes.c_void_p), ('d_replay', ctypes.c_void_p), ('replay_env', ctypes.c_int32),
                 ('d_status', ctypes.c_void_p), ('sm_limit', ctypes.c_int32),
-                ('widths', ctypes.c_void_p), ('n_widths', ctypes.c_int32), ('d_sensor_noise', ctypes.c_void_p)]
+                ('widths', ctypes.c_void_p), ('n_widths', ctypes.c_int32), ('d_sensor_noise', ctypes.c_void_p),
+                ('flags', ctypes.c_int32)]
 
 
 REPLAY_COLS = 20
 STATUS_NONFINITE = 1
+STATUS_GUST_FLAG = 2
+ROLLOUT_GUST = 1
 ACTIVATIONS = {'tanh': 0, 'elu': 1, 'relu': 2}
 _lib = None
 

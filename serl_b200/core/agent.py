@@ -102,7 +102,10 @@ class Agent:
 
     def _eval_kw(self):
         env = self.env
-        return {} if env.t_max == 20 else {'t_max': float(env.t_max), 'smooth_width': refsig.widths(env.t_max)[1]}
+        kw = {} if env.t_max == 20 else {'t_max': float(env.t_max), 'smooth_width': refsig.widths(env.t_max)[1]}
+        if env.mode_code & rollout.MODE_GUST:
+            kw['gust'] = True
+        return kw
 
     def _fly(self, agent, n, is_action_noise=False, store_transition=False, trace=False, stream=None, copy_genome=False, draws=None) -> _Flight:
         """launch n episodes of one actor (fresh reference signals each, or the given `draws`) without waiting for them."""

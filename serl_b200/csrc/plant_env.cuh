@@ -317,15 +317,28 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
 // tcgen05 transfers are warp-collective: with TMF EVERY lane of the warp must make the call; lanes whose trajectory is
 // over pass active = false and keep their state.  (Builds with a float right-hand side and traced episodes, which hand
 // all six stages to the navigation integrator, use the local-memory form.)
-template <bool STAB = false, bool TMF = false>
+// GUST instantiation (launches with a `gust` env, SERL_MODE_GUST): bit 30 of `call` marks a gust env, and u[3], the
+// right-hand side's angle-of-attack offset, is atan(w_gust / V) for the stages whose time lies in the pulse 20 s <= t <= 23 s
+// (include/serl_b200.h).  Without GUST the offset is the constant 0 and the code is that of a build without the feature.
+#define PLANT_CALL_GUST (1 << 30)
+__device__ __forceinline__ real plant_gust_offset(int call, int s, real V)
+{
+    const bool on = (call == SERL_TRIGGER_CALLS - 1 && s == 5) || (call >= SERL_TRIGGER_CALLS && call < SERL_GUST_END_CALLS) ||
+                    (call == SERL_GUST_END_CALLS && s == 0);
+    if (!on) return (real)0;
+    return (real)(atan(PLANT_DIV((double)SERL_GUST_W, (double)V)) * 1.0);
+}
+template <bool STAB = false, bool TMF = false, bool GUST = false>
 static __device__ __noinline__ void plant_step(const real* pv, double* X, const double* U, const real* tab, bool nav = false,
                                                const real* pv_post = nullptr, int call = 0, uint32_t taddr = 0, bool active = true)
 {
+    const bool gust = GUST && (call & PLANT_CALL_GUST) != 0;
+    if (GUST) call &= ~PLANT_CALL_GUST;
     constexpr double h = 0.01;
     constexpr double B[6][6] = ODE5_B_INIT;
     constexpr int LIVE[NLIVE] = ODE5_LIVE_INIT;
-    real x[NLIVE], u[3];
-    u[0] = (real)U[0]; u[1] = (real)U[1]; u[2] = (real)U[2];
+    real x[NLIVE], u[4];
+    u[0] = (real)U[0]; u[1] = (real)U[1]; u[2] = (real)U[2]; u[3] = (real)0;
 #pragma unroll
     for (int li = 0; li < NLIVE; ++li) x[li] = (real)X[LIVE[li]];
     double xl[NLIVE];
@@ -334,6 +347,7 @@ static __device__ __noinline__ void plant_step(const real* pv, double* X, const 
 #pragma unroll
         for (int s = 0; s < 6; ++s) {
             const bool post = pv_post != nullptr && (call >= SERL_TRIGGER_CALLS || (s == 5 && call == SERL_TRIGGER_CALLS - 1));
+            if (GUST) u[3] = gust ? plant_gust_offset(call, s, x[3]) : (real)0;
             if (STAB) plant_rhs_common_smem(x, u, fc, tab, post ? pv_post : pv);
             else plant_rhs_common(x, u, fc, tab, post ? pv_post : pv);
             double acc[NLIVE];
@@ -376,6 +390,7 @@ static __device__ __noinline__ void plant_step(const real* pv, double* X, const 
 #pragma unroll
         for (int s = 0; s < 6; ++s) {
             const bool post = pv_post != nullptr && (call >= SERL_TRIGGER_CALLS || (s == 5 && call == SERL_TRIGGER_CALLS - 1));
+            if (GUST) u[3] = gust ? plant_gust_offset(call, s, x[3]) : (real)0;
             if (STAB) plant_rhs_common_smem(x, u, f[s], tab, post ? pv_post : pv);
             else plant_rhs_common(x, u, f[s], tab, post ? pv_post : pv);
 #pragma unroll
@@ -460,7 +475,7 @@ struct Env {
     const double* ref_st;
     double t, ret, theta_trim;
     int fault, k;
-    bool done;
+    bool done, gust;         // gust: SERL_MODE_GUST
 };
 
 #define DEG2RAD 0.017453292519943295   // numpy deg2rad multiplier (pi/180)
@@ -484,6 +499,7 @@ __device__ __forceinline__ void env_bind(Env& e, const RolloutArgs& a, int env, 
     const int post = (mode >> 16) & 0xff;
     e.pv_post = post ? pv_base + post * PLANT_NPV : nullptr;
     e.fault = (mode >> 8) & 0xff;
+    e.gust = (mode & SERL_MODE_GUST) != 0;
     e.ref_lv = a.ref_levels + (size_t)env * 2 * SERL_REF_BLOCKS;
     e.ref_st = a.ref_starts + (size_t)env * 2 * SERL_REF_BLOCKS;
     // theta_trim = rad2deg(theta) of reset()'s step output (phlabenv.py:317) — with the sensor-noise shim that output is noisy
@@ -523,14 +539,14 @@ static __device__ void env_reset(Env& e, const RolloutArgs& a, int env, float* o
     obs[3] = (float)x0[0]; obs[4] = (float)x0[1]; obs[5] = (float)x0[2]; obs[6] = (float)x0[4];
     double U[3] = {0.0, 0.0, 0.0}, cmd[3];
     apply_fault(e.fault, U, cmd);
-    plant_step<STAB>(e.pv, e.X, cmd, e.tab, a.trace != nullptr, e.pv_post, 0);
+    plant_step<STAB>(e.pv, e.X, cmd, e.tab, a.trace != nullptr, e.pv_post, 0);      // call 0: no gust stage
     e.t = 0.0; e.ret = 0.0; e.k = 0; e.done = false;
 }
 
 // one CitationEnv.step (phlabenv.py:430-482) + the bookkeeping of Agent.evaluate (agent.py:85-118)
 // TMF (stage derivatives in tensor memory, see plant_step): the whole warp makes the call; lanes with active = false go
 // through the plant's collective transfers and change nothing.
-template <bool STAB = false, bool TMF = false>
+template <bool STAB = false, bool TMF = false, bool GUST = false>
 static __device__ void env_step(Env& e, const RolloutArgs& ar, size_t traj, int actor, bool replay, const float* a, float* obs,
                                 bool active = true, uint32_t taddr = 0)
 {
@@ -563,7 +579,7 @@ static __device__ void env_step(Env& e, const RolloutArgs& ar, size_t traj, int 
     double xo[12];
 #pragma unroll
     for (int i = 0; i < 12; ++i) xo[i] = e.X[i];
-    plant_step<STAB, TMF>(e.pv, e.X, cmd, e.tab, ar.trace != nullptr, e.pv_post, e.k + 1, taddr, active);
+    plant_step<STAB, TMF, GUST>(e.pv, e.X, cmd, e.tab, ar.trace != nullptr, e.pv_post, (e.k + 1) | (GUST && e.gust ? PLANT_CALL_GUST : 0), taddr, active);
     if (!active) return;
     sensor_noise(ar, traj, e.k + 1, xo);
 

@@ -279,7 +279,9 @@ __global__ void genome_layout_kernel(const float* __restrict__ w, float* __restr
 // named barrier only to swap the genome, which ONE elected thread brings in with a bulk TMA copy.
 // TABS: plant tables staged in shared memory (true) or read from global memory through L1 (false: h = 128, whose
 // 207 KB genome leaves no room for them).
-template <int H, bool TABS>
+// GUST: the launch contains envs of the gust build (serl_rollout_desc.flags & SERL_ROLLOUT_GUST); the training instantiation
+// carries no trace of the feature (a gust env in it raises SERL_STATUS_GUST_FLAG)
+template <int H, bool TABS, bool GUST>
 __global__ void __launch_bounds__(MAX_CTA_THREADS, 1)
 rollout_kernel_persist(RolloutArgs ar)
 {
@@ -437,6 +439,7 @@ rollout_kernel_persist(RolloutArgs ar)
                 traj = (size_t)actor * ar.n_envs + env;
                 if (valid) {
                     env_bind(e, ar, env, pv_base, traj);
+                    if (!GUST && e.gust && ar.status) atomicOr(ar.status, SERL_STATUS_GUST_FLAG);
                     if (from_h) {
                         const long long hx = (slot - 1) * slot_threads + wslot * 32 + lane;
 #pragma unroll
@@ -450,7 +453,7 @@ rollout_kernel_persist(RolloutArgs ar)
                         env_reset<TABS>(e, ar, env, obs, traj);
                     }
                 } else {
-                    e.done = true; e.k = 0; e.ret = 0.0; e.t = 0.0; e.fault = 0; e.pv = pv_base; e.pv_post = nullptr; e.theta_trim = 0.0;
+                    e.done = true; e.k = 0; e.ret = 0.0; e.t = 0.0; e.fault = 0; e.gust = false; e.pv = pv_base; e.pv_post = nullptr; e.theta_trim = 0.0;
                     e.ref_lv = ar.ref_levels; e.ref_st = ar.ref_starts;
 #pragma unroll
                     for (int i = 0; i < NX; ++i) e.X[i] = 0.0;
@@ -471,8 +474,8 @@ rollout_kernel_persist(RolloutArgs ar)
             else actor_forward_warp<H, SERL_ACT_LEAKY_RELU>(w, L, lane, obs, a);
             // with the stage derivatives in tensor memory the plant's transfers are warp-collective: every lane steps,
             // lanes whose trajectory is over change nothing
-            if (use_tmem) env_step<TABS, true>(e, ar, traj, actor, replay, a, obs, mine, taddr);
-            else if (mine) env_step<TABS, false>(e, ar, traj, actor, replay, a, obs);
+            if (use_tmem) env_step<TABS, true, GUST>(e, ar, traj, actor, replay, a, obs, mine, taddr);
+            else if (mine) env_step<TABS, false, GUST>(e, ar, traj, actor, replay, a, obs);
         }
     }
     if (use_tmem) {                                    // every warp has left the loop (it ends at a CTA barrier)
@@ -507,7 +510,7 @@ rollout_kernel_simple(RolloutArgs ar)
     const bool replay = ar.replay != nullptr && env == ar.replay_env;
     while (!e.done) {
         actor_forward_simple(w, ar.sh, bufA, bufB, tid, 128, obs, a);
-        env_step(e, ar, traj, actor, replay, a, obs);
+        env_step<false, false, true>(e, ar, traj, actor, replay, a, obs);       // (the gust schedule costs nothing that matters here)
     }
     ar.returns[traj] = e.ret;
     ar.steps[traj] = e.k;
@@ -576,7 +579,8 @@ __global__ void plant_step_kernel(double* __restrict__ X, const double* __restri
     for (int k = 0; k < NX; ++k) x[k] = X[(size_t)i * NX + k];
     u[0] = cmd[3 * i]; u[1] = cmd[3 * i + 1]; u[2] = cmd[3 * i + 2];
     const int post = (variant[i] >> 16) & 0xff;
-    plant_step(plant_pv[variant[i] & 0xff], x, u, plant_tables_blob, false, post ? plant_pv[post] : nullptr, call ? call[i] : 0);
+    plant_step<false, false, true>(plant_pv[variant[i] & 0xff], x, u, plant_tables_blob, false, post ? plant_pv[post] : nullptr,
+                                   (call ? call[i] : 0) | ((variant[i] & SERL_MODE_GUST) ? PLANT_CALL_GUST : 0));
 #pragma unroll
     for (int k = 0; k < NX; ++k) X[(size_t)i * NX + k] = x[k];
 }
@@ -1011,7 +1015,7 @@ static cudaError_t scratch_get(cudaStream_t s, size_t bytes, void** out, int whi
     return cudaSuccess;
 }
 
-template <int H, bool TABS>
+template <int H, bool TABS, bool GUST = false>
 static cudaError_t launch_persist(RolloutArgs& ar, int apc_max, cudaStream_t s, void** scratch)
 {
     constexpr int TABN2 = (PT_TOTAL + SERL_PLANT_COUNT * PLANT_NPV + 1) & ~1;
@@ -1054,9 +1058,9 @@ static cudaError_t launch_persist(RolloutArgs& ar, int apc_max, cudaStream_t s, 
     genome_layout_kernel<<<lay_grid, 256, 0, s>>>(ar.weights, wt, ar.pop, ar.P, ar.P4, ar.sh.state_dim, H, ar.sh.num_layers);
     serl_count_launch();
     const size_t smem = (TABS ? (size_t)TABN2 * sizeof(real) : 0) + (size_t)apc * ar.P4 * 4;
-    e = cudaFuncSetAttribute(rollout_kernel_persist<H, TABS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(rollout_kernel_persist<H, TABS, GUST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    rollout_kernel_persist<H, TABS><<<(unsigned)grid, apc * wps * 32, smem, s>>>(ar);
+    rollout_kernel_persist<H, TABS, GUST><<<(unsigned)grid, apc * wps * 32, smem, s>>>(ar);
     serl_count_launch();
     return cudaGetLastError();
 }
@@ -1102,11 +1106,14 @@ static int rollout_impl(const serl_rollout_desc& d, void* stream)
         if (apc_max > 4) apc_max = 4;
         if (apc_max > 2 && H > 32) apc_max = 2;
         void* scratch = nullptr;
-        if (H == 32) e = launch_persist<32, true>(ar, apc_max, s, &scratch);
-        else if (H == 64) e = launch_persist<64, true>(ar, apc_max, s, &scratch);
-        else if (H == 72) e = launch_persist<72, true>(ar, apc_max, s, &scratch);
-        else if (H == 96) e = launch_persist<96, true>(ar, apc_max, s, &scratch);
-        else e = tabs ? launch_persist<128, true>(ar, apc_max, s, &scratch) : launch_persist<128, false>(ar, apc_max, s, &scratch);
+        const bool gust = (d.flags & SERL_ROLLOUT_GUST) != 0;
+#define K1_LAUNCH(HH, TT) (gust ? launch_persist<HH, TT, true>(ar, apc_max, s, &scratch) : launch_persist<HH, TT, false>(ar, apc_max, s, &scratch))
+        if (H == 32) e = K1_LAUNCH(32, true);
+        else if (H == 64) e = K1_LAUNCH(64, true);
+        else if (H == 72) e = K1_LAUNCH(72, true);
+        else if (H == 96) e = K1_LAUNCH(96, true);
+        else e = tabs ? K1_LAUNCH(128, true) : K1_LAUNCH(128, false);
+#undef K1_LAUNCH
     } else {
         const size_t smem = (size_t)ar.P4 * 4 + 2ull * H * 128 * 4;
         if (smem > 227 * 1024) return serl_fail(SERL_ERR_UNSUPPORTED, "serl_rollout: genome + activations exceed 227 KB of shared memory");

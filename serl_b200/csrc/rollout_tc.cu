@@ -404,6 +404,9 @@ rollout_kernel_tc(TcArgs ar)
     const RolloutArgs& r = ar.r;
     const real* tab = reinterpret_cast<const real*>(smem_raw);
     const real* pv_base = tab + PT_TOTAL;
+    int gust_mine = 0;
+    for (int i = threadIdx.x; i < r.n_envs; i += blockDim.x) gust_mine |= r.env_mode[i] & SERL_MODE_GUST;
+    const bool any_gust = __syncthreads_or(gust_mine) != 0;      // does any env of the launch fly the gust build?
     const int tid = c.gtid;
     const int n_stages = ar.w1 / TC_KSLAB;
     // the two groups of a CTA run independent task loops
@@ -421,7 +424,7 @@ rollout_kernel_tc(TcArgs ar)
             env_bind(e, r, env, pv_base, (size_t)actor * r.n_envs + env);
             env_reset<true>(e, r, env, obs, (size_t)actor * r.n_envs + env);
         } else {
-            e.done = true; e.k = 0; e.ret = 0.0; e.t = 0.0; e.fault = 0; e.pv = pv_base; e.pv_post = nullptr; e.theta_trim = 0.0;
+            e.done = true; e.k = 0; e.ret = 0.0; e.t = 0.0; e.fault = 0; e.gust = false; e.pv = pv_base; e.pv_post = nullptr; e.theta_trim = 0.0;
             e.ref_lv = r.ref_levels; e.ref_st = r.ref_starts;
 #pragma unroll
             for (int i = 0; i < NX; ++i) e.X[i] = 0.0;
@@ -432,7 +435,10 @@ rollout_kernel_tc(TcArgs ar)
         const bool replay = valid && r.replay != nullptr && env == r.replay_env;
         while (group_any(c.grp, !e.done)) {
             tc_actor_forward<ACT>(c, ar, tiles_actor, obs, a);
-            if (!e.done) env_step<true>(e, r, traj, actor, replay, a, obs);
+            if (!e.done) {
+                if (any_gust) env_step<true, false, true>(e, r, traj, actor, replay, a, obs);
+                else env_step<true>(e, r, traj, actor, replay, a, obs);
+            }
         }
         if (valid) {
             r.returns[traj] = e.ret;

@@ -50,11 +50,12 @@ class CitationEnv:
         alias = {'high-q': 'h2000-v150', 'low-q': 'h10000-v90', 'cg-aft': 'cg', 'cg-shift': 'cg-timed'}
         m = alias.get(m, m)
         # 'noise' (envs/phlabenv.py:139-142): the nominal plant behind the sensor-noise shim (envs/noise/citation.py:72-82)
-        self.sensor_noise = m == 'noise'
-        if self.sensor_noise:
+        # 'gust' (:165-169): the gust build (nominal dynamics + a vertical gust for 20 s <= t <= 23 s) behind the same shim
+        self.sensor_noise = m in ('noise', 'gust')
+        if m == 'noise':
             m = 'nominal'
-        if m in ('gust', 'test'):
-            raise ValueError("mode '%s': the gust / test plant builds are not lifted (DESIGN.md: out of scope)" % m)
+        if m == 'test':
+            raise ValueError("mode 'test': the test plant build is not lifted (DESIGN.md: out of scope)")
         if m not in rollout.MODES:
             raise ValueError('Unknown trim condition or control mode!')
         self.mode = m
@@ -175,7 +176,7 @@ class CitationEnv:
         dcmd = torch.as_tensor(cmd[:3].reshape(1, 3), device=self._X.device)
         if self.mode_code >> 16:          # time-triggered build: the plant needs its clock (native calls made so far)
             call = torch.tensor([self._calls], dtype=torch.int32, device=self._X.device)
-            var = torch.tensor([(self.mode_code & 0xff) | (self.mode_code & 0xff0000)], dtype=torch.int32, device=self._X.device)
+            var = torch.tensor([self.mode_code & ~0xff00], dtype=torch.int32, device=self._X.device)     # without the fault field
             self._plant('serl_plant_step_timed', ctypes.c_void_p(self._X.data_ptr()), ctypes.c_void_p(dcmd.data_ptr()),
                         ctypes.c_void_p(var.data_ptr()), ctypes.c_void_p(call.data_ptr()), 1)
         else:

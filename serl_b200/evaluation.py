@@ -43,7 +43,8 @@ def validate_agent(genome, shape, env, user_refs_lst, num_trails=1, device=None)
     if getattr(env, 'sensor_noise', False):
         noise = torch.as_tensor(sensor_noise_draws(n, horizon).reshape(1, n, horizon + 1, 7), device=dev)
     r = rollout.population_rollout(g, shape, torch.as_tensor(levels, device=dev), torch.as_tensor(starts, device=dev), md,
-                                   horizon=horizon, trace=True, t_max=float(env.t_max), smooth_width=smooth_w, sensor_noise=noise)
+                                   horizon=horizon, trace=True, t_max=float(env.t_max), smooth_width=smooth_w, sensor_noise=noise,
+                                   gust=bool(env.mode_code & rollout.MODE_GUST))
     torch.cuda.synchronize()
     r.check()
     steps = r.steps[0].cpu().numpy()

@@ -20,13 +20,15 @@ MODES = {
     'sa': ('h2000_v90', 'sa'), 'se': ('h2000_v90', 'se'), 'ice': ('ice', 'none'), 'cg': ('cg', 'none'),
     'cg-for': ('cg_for', 'none'), 'h2000-v150': ('h2000_v150', 'none'), 'h10000-v90': ('h10000_v90', 'none'),
     'cg-timed': ('cg_timed', 'none'),
+    'gust': ('h2000_v90', 'none'),      # nominal dynamics + MODE_GUST (include/serl_b200.h); the env adds the sensor-noise shim
 }
+MODE_GUST = 1 << 24
 
 
 def mode_code(mode):
     v, f = MODES[mode]
     post = PLANT_VARIANTS.index(POST_VARIANT[v]) if v in POST_VARIANT else 0
-    return PLANT_VARIANTS.index(v) | (FAULTS.index(f) << 8) | (post << 16)
+    return PLANT_VARIANTS.index(v) | (FAULTS.index(f) << 8) | (post << 16) | (MODE_GUST if mode == 'gust' else 0)
 
 
 def actor_shape(hidden, num_layers=3, activation='tanh', state_dim=7, action_dim=3):
@@ -53,7 +55,10 @@ class RolloutResult:
 
     def check(self):
         """raise if the kernel flagged a non-finite trajectory (synchronises the device)."""
-        if self.status is not None and int(self.status.item()) & _native.STATUS_NONFINITE:
+        st = int(self.status.item()) if self.status is not None else 0
+        if st & _native.STATUS_GUST_FLAG:
+            raise _native.NativeError("serl_rollout: an env has mode 'gust' but the launch was not made with gust=True")
+        if st & _native.STATUS_NONFINITE:
             raise _native.NativeError('serl_rollout: a trajectory produced a non-finite state / return (status flag)')
 
 
@@ -69,7 +74,7 @@ def variant_sorted_order(env_mode):
 
 def population_rollout(weights, shape, ref_levels, ref_starts, env_mode, horizon=HORIZON, trace=False, out=None, action_noise=None,
                        actions=False, t_max=None, smooth_width=None, env_order=None, replay_env=None, status=True, sm_limit=0,
-                       fitness=True, widths=None, sensor_noise=None):
+                       fitness=True, widths=None, sensor_noise=None, gust=False):
     """weights [pop,P] fp32 cuda; ref_levels/ref_starts [n_envs,2,6] f64 cuda; env_mode [n_envs] int32 cuda.
     env_order: optional int32 [n_envs] permutation (see variant_sorted_order); replay_env: record the transitions of that env
     of every actor into result.replay [pop, horizon, REPLAY_COLS]; status: carry the device status word (result.check());
@@ -124,6 +129,7 @@ def population_rollout(weights, shape, ref_levels, ref_starts, env_mode, horizon
     if sensor_noise is not None:      # envs/noise/citation.py:72-82: standard-normal draws [pop, n_envs, horizon + 1, 7]
         assert sensor_noise.shape == (pop, n_envs, horizon + 1, 7) and sensor_noise.dtype == torch.float32 and sensor_noise.is_contiguous()
         d.d_sensor_noise = p(sensor_noise)
+    d.flags = _native.ROLLOUT_GUST if gust else 0       # some env flies the gust build (mode_code(...) & MODE_GUST)
     if widths:
         warr = (ctypes.c_int32 * len(widths))(*[int(x) for x in widths])
         d.widths, d.n_widths = ctypes.cast(warr, ctypes.c_void_p), len(widths)

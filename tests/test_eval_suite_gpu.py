@@ -101,8 +101,10 @@ def test_noise_mode_and_time_triggered_modes_are_named():
     from serl_b200.envs import config
     assert config.select_env('PHlab_attitude_noise').sensor_noise
     assert config.select_env('PHlab_attitude_cg-shift').mode == 'cg-timed'
+    gust = config.select_env('PHlab_attitude_gust')
+    assert gust.sensor_noise and gust.mode == 'gust' and gust.mode_code & (1 << 24)
     with pytest.raises(ValueError):
-        config.select_env('PHlab_attitude_gust')
+        config.select_env('PHlab_attitude_test')
 
 
 @pytest.mark.skipif(not os.path.exists(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'oracle', '_ref', 'citation_cg_timed.so')),
@@ -139,3 +141,49 @@ def test_cg_timed_build_switches_at_20_s_like_the_reference_binary():
     nominal = run('nominal')
     assert np.array_equal(nominal.trace_x[0, 0, :1999].cpu().numpy()[:, live], tx[:1999, live])        # identical before the trigger
     assert np.abs(nominal.trace_x[0, 0, 2100:2400].cpu().numpy()[:, live] - tx[2100:2400, live]).max() > 1e-5
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'oracle', '_ref', 'citation_gust.so')),
+                    reason='needs the reference gust binary under oracle/_ref')
+def test_gust_build_flies_the_pulse_like_the_reference_binary():
+    """envs/gust ('Vertical Gust of 15ft/s at 20s', envs/phlabenv.py:165-169): nominal dynamics, and for 20 s <= t <= 23 s the
+    aerodynamic angle of attack is alpha - atan(w / V).  A 30 s episode (3001 steps, sensor noise off) through the kernel vs the
+    reference binary stepped by the oracle env; the untraced launch (stage derivatives in tensor memory) must return the same bits
+    as the traced one (local memory)."""
+    from serl_b200 import rollout
+    dev = torch.device('cuda:0')
+    g = ACT['serl10_elite_h72_tanh']
+    lv, st = refsig.make_ref_params(1, seed_base=41, t_max=30)
+    md = lambda m: torch.tensor([rollout.mode_code(m)], dtype=torch.int32, device=dev)
+    run = lambda m, trace: rollout.population_rollout(torch.as_tensor(g[None], device=dev), rollout.actor_shape(72), torch.as_tensor(lv, device=dev),
+                                                      torch.as_tensor(st, device=dev), md(m), horizon=3001, trace=trace, t_max=30.0, smooth_width=4.5,
+                                                      gust=m == 'gust')
+    r = run('gust', True)
+    torch.cuda.synchronize()
+    r.check()
+    env = phlab.CitationEnv('gust', 'ref', t_max=30)
+    env.smooth_w = 4.5
+    obs = env.reset(lv[0], st[0])
+    tot, xs = 0.0, []
+    for k in range(3001):
+        obs, rew, done, _ = env.step(KOActor(g).select_action(obs))
+        xs.append(env.x.copy())
+        tot += rew
+        if done:
+            break
+    assert int(r.steps[0, 0]) == k + 1
+    tx = r.trace_x[0, 0, :k + 1].cpu().numpy()
+    live = [0, 1, 2, 3, 4, 5, 6, 7, 9]
+    err = np.abs(tx[:, live] - np.asarray(xs)[:, live]).max(axis=1)
+    assert err.max() < 1e-8, (int(err.argmax()), float(err.max()), err[1995:2005], err[2295:2305])
+    assert abs(float(r.returns[0, 0]) - tot) <= 1e-8 * abs(tot)
+    nominal = run('nominal', True)
+    assert np.array_equal(nominal.trace_x[0, 0, :1999].cpu().numpy()[:, live], tx[:1999, live])        # identical before the gust
+    assert np.abs(nominal.trace_x[0, 0, 2100:2300].cpu().numpy()[:, live] - tx[2100:2300, live]).max() > 1e-4
+    fast = run('gust', False)
+    assert torch.equal(fast.returns, r.returns) and torch.equal(fast.steps, r.steps)
+    # a gust env in a launch made without the flag is reported, not silently flown as nominal
+    bad = rollout.population_rollout(torch.as_tensor(g[None], device=dev), rollout.actor_shape(72), torch.as_tensor(lv, device=dev),
+                                     torch.as_tensor(st, device=dev), md('gust'), horizon=50)
+    with pytest.raises(Exception, match='gust'):
+        bad.check()

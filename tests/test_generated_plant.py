@@ -49,9 +49,9 @@ typedef %(real)s real;
 #include "%(gen)s/plant_rhs_common.h"
 #include "%(gen)s/plant_rhs_nav.h"
 void dev_rhs(int variant, const double* Xd, const double* Ud, double* out) {
-    real X[19], U[3], xdot[19], nav[19];
+    real X[19], U[4], xdot[19], nav[19];          /* U[3]: angle-of-attack offset of the gust build (0 otherwise) */
     for (int i = 0; i < 19; ++i) { X[i] = (real)Xd[i]; xdot[i] = 0; }
-    for (int i = 0; i < 3; ++i) U[i] = (real)Ud[i];
+    for (int i = 0; i < 4; ++i) U[i] = (real)Ud[i];
     plant_rhs_common(X, U, xdot, plant_tables_blob, plant_pv[variant]);      /* one function for every variant */
     plant_rhs_nav(X, U, nav, plant_tables_blob);
     xdot[8] = nav[8]; xdot[10] = nav[10]; xdot[11] = nav[11];
@@ -85,7 +85,7 @@ def test_generated_device_rhs_matches_reference_binary_vectors(devlib, variant):
     worst = 0.0
     for x, u, f in zip(KAT[variant + '_X'], KAT[variant + '_U'], KAT[variant + '_F']):
         xd = (D * 19)()
-        lib.dev_rhs(v, (D * 19)(*x), (D * 3)(*u), xd)
+        lib.dev_rhs(v, (D * 19)(*x), (D * 4)(*u, 0.0), xd)
         got = np.array(xd[:])
         idx = LIVE + [8, 10, 11]
         if which == 'gen_exact':
@@ -94,6 +94,67 @@ def test_generated_device_rhs_matches_reference_binary_vectors(devlib, variant):
         worst = max(worst, err.max())
     # fast mode (reciprocal tables / constants, merged rows): 1e-11; single-precision right-hand side: float round-off
     assert worst < (5e-4 if which == 'gen_f32' else 1e-11), worst
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/envs'), reason='needs the reference tree (build container only)')
+def test_gust_build_is_the_nominal_rhs_with_an_angle_of_attack_offset(devlib, tmp_path):
+    """envs/gust ("vertical gust of 15 ft/s at 20 s"): ode5 over the generated right-hand side with U[3] = atan(w / V) for the
+    stages inside 20 s <= t <= 23 s (last stage of native call 1999, calls 2000..2299, first stage of call 2300) reproduces
+    the gust BINARY bit for bit (reference-order build) through both edges of the pulse."""
+    import math
+    import shutil
+    which, lib = devlib
+    if which == 'gen_f32':
+        pytest.skip('double-precision check')
+    D = ctypes.c_double
+    so = tmp_path / 'gust.so'
+    shutil.copy('/root/reference/envs/gust/_citation.cpython-38-x86_64-linux-gnu.so', so)
+    ref = ctypes.CDLL(str(so))
+    ref.step.argtypes = [ctypes.POINTER(D), ctypes.POINTER(D)]
+    ref.initialize()
+    rtx = (D * 19).in_dll(ref, 'rtX')
+    B = [[1 / 5, 0, 0, 0, 0, 0], [3 / 40, 9 / 40, 0, 0, 0, 0], [44 / 45, -56 / 15, 32 / 9, 0, 0, 0],
+         [19372 / 6561, -25360 / 2187, 64448 / 6561, -212 / 729, 0, 0], [9017 / 3168, -355 / 33, 46732 / 5247, 49 / 176, -5103 / 18656, 0],
+         [35 / 384, 0, 500 / 1113, 125 / 192, -2187 / 6784, 11 / 84]]
+    idx = LIVE + [8, 10, 11]
+    w = float.fromhex('0x1.249ba5e353f7dp+2')          # include/serl_b200.h SERL_GUST_W
+    h = 0.01
+
+    def on(call, s):
+        return (call == 1999 and s == 5) or (2000 <= call < 2300) or (call == 2300 and s == 0)
+
+    def step(X, u, call):
+        f, x = [], X.copy()
+        for s in range(6):
+            out = (D * 19)()
+            lib.dev_rhs(0, (D * 19)(*x), (D * 4)(u[0], u[1], u[2], math.atan(w / x[3]) * 1.0 if on(call, s) else 0.0), out)
+            f.append(np.array(out[:]))
+            x = X.copy()
+            for i in idx:
+                acc = f[0][i] * (h * B[s][0])
+                for j in range(1, s + 1):
+                    acc += f[j][i] * (h * B[s][j])
+                x[i] = X[i] + acc
+        return x
+    cmd, out = (D * 10)(), (D * 12)()
+    X = np.array(rtx[:])
+    worst, active = 0.0, 0
+    for k in range(2306):
+        c = 0.02 * np.sin(0.01 * k + np.arange(3))
+        cmd[0], cmd[1], cmd[2] = c
+        window = 1996 <= k <= 2003 or 2296 <= k <= 2303 or k == 2150
+        Xn = step(X, c, k) if window else None
+        ref.step(cmd, out)
+        Xb = np.array(rtx[:])
+        if window:
+            err = np.abs(Xn[idx] - Xb[idx]).max()
+            worst = max(worst, err / np.abs(Xb[idx]).max())
+            if which == 'gen_exact':
+                assert err == 0.0, (k, err)
+            nominal = step(X, c, -1)
+            active += int(np.abs(nominal[idx] - Xb[idx]).max() > 0)
+        X = Xb
+    assert worst < 1e-12 and active >= 10        # fast build: <= 1 ulp per operation; the gust really is on in the window
 
 
 @pytest.mark.skipif(not os.path.isdir('/root/reference/envs'), reason='needs the reference tree (build container only)')

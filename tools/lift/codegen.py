@@ -229,7 +229,7 @@ class Emitter:
                 cid, side = guards[n.id]
                 call = 'PLANT_EXP(%s)' % r(a[0]) if op == 'exp' else 'PLANT_POW(%s, %s)' % (r(a[0]), r(a[1]))
                 L.append('%s %s = 0.0; if (%sv%d) %s = %s;' % (R, v, '' if side == 1 else '!', cid, v, call))
-            elif op in ('sin', 'cos', 'tan', 'exp', 'log10'):
+            elif op in ('sin', 'cos', 'tan', 'exp', 'log10', 'atan', 'asin', 'acos'):
                 L.append('const %s %s = PLANT_%s(%s);' % (R, v, op.upper(), r(a[0])))
             elif op == 'pow':
                 L.append('const %s %s = PLANT_POW(%s, %s);' % (R, v, r(a[0]), r(a[1])))

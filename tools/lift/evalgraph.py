@@ -99,7 +99,7 @@ class Evaluator:
                     v = a[1] if a[0] else 0.0
                 elif op == 'mandn':
                     v = 0.0 if a[0] else a[1]
-                elif op in ('sin', 'cos', 'tan', 'exp', 'log10'):
+                elif op in ('sin', 'cos', 'tan', 'exp', 'log10', 'atan', 'asin', 'acos'):
                     v = getattr(math, op)(a[0])
                 elif op == 'pow':
                     v = _libm.pow(a[0], a[1])
