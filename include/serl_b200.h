@@ -41,6 +41,8 @@ enum { SERL_PLANT_H2000_V90 = 0, SERL_PLANT_ICE = 1, SERL_PLANT_CG = 2, SERL_PLA
  * 20 s <= t <= 23 s (stage times of the ode5 step: the last stage of native call 1999, calls 2000..2299, the first stage of
  * call 2300); checked bit for bit against the binary on the CPU, tests/test_generated_plant.py */
 #define SERL_MODE_GUST (1 << 24)
+#define SERL_MODE_GUST_UP (1 << 25)    /* with SERL_MODE_GUST: the `test` build (envs/test), the same pulse with the opposite sign:
+                                         alpha + atan(w_gust / V); also bit-exact against its binary */
 #define SERL_GUST_END_CALLS 2300
 #define SERL_GUST_W 0x1.249ba5e353f7dp+2      /* 4.572 m/s = 15 ft/s, the literal of the gust binary */
 enum { SERL_FAULT_NONE = 0, SERL_FAULT_BE = 1, SERL_FAULT_JR = 2, SERL_FAULT_SA = 3, SERL_FAULT_SE = 4 };

@@ -13,7 +13,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_ENVS = '/root/reference/envs'
 VARIANTS = ['h2000_v90', 'ice', 'cg', 'cg_for', 'h2000_v150', 'h10000_v90']
-REF_ONLY = ['cg_timed', 'gust']       # time-triggered builds: checked against their binaries only (no C restatement)
+REF_ONLY = ['cg_timed', 'gust', 'test']       # time-triggered builds: checked against their binaries only (no C restatement)
 LIB = os.path.join(HERE, '_build', 'libplant_oracle.so')
 
 

@@ -25,6 +25,7 @@ MODES = {
     'cg-for': ('cg_for', 'none'), 'h2000-v150': ('h2000_v150', 'none'), 'h10000-v90': ('h10000_v90', 'none'),
     'cg-timed': ('cg_timed', 'none'),       # time-triggered build: reference binary only, one episode at a time (own clock)
     'gust': ('gust', 'none'),               # likewise (envs/gust: vertical gust for 20 s <= t <= 23 s + the sensor-noise shim)
+    'test': ('test', 'none'),               # envs/test: the same pulse with the opposite sign
 }
 FAULTS = ['none', 'be', 'jr', 'sa', 'se']
 

@@ -321,6 +321,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
 // right-hand side's angle-of-attack offset, is atan(w_gust / V) for the stages whose time lies in the pulse 20 s <= t <= 23 s
 // (include/serl_b200.h).  Without GUST the offset is the constant 0 and the code is that of a build without the feature.
 #define PLANT_CALL_GUST (1 << 30)
+#define PLANT_CALL_GUST_UP (1 << 29)       // the `test` build: the same pulse with the opposite sign
 __device__ __forceinline__ real plant_gust_offset(int call, int s, real V)
 {
     const bool on = (call == SERL_TRIGGER_CALLS - 1 && s == 5) || (call >= SERL_TRIGGER_CALLS && call < SERL_GUST_END_CALLS) ||
@@ -332,8 +333,8 @@ template <bool STAB = false, bool TMF = false, bool GUST = false>
 static __device__ __noinline__ void plant_step(const real* pv, double* X, const double* U, const real* tab, bool nav = false,
                                                const real* pv_post = nullptr, int call = 0, uint32_t taddr = 0, bool active = true)
 {
-    const bool gust = GUST && (call & PLANT_CALL_GUST) != 0;
-    if (GUST) call &= ~PLANT_CALL_GUST;
+    const bool gust = GUST && (call & PLANT_CALL_GUST) != 0, gust_up = GUST && (call & PLANT_CALL_GUST_UP) != 0;
+    if (GUST) call &= ~(PLANT_CALL_GUST | PLANT_CALL_GUST_UP);
     constexpr double h = 0.01;
     constexpr double B[6][6] = ODE5_B_INIT;
     constexpr int LIVE[NLIVE] = ODE5_LIVE_INIT;
@@ -347,7 +348,7 @@ static __device__ __noinline__ void plant_step(const real* pv, double* X, const 
 #pragma unroll
         for (int s = 0; s < 6; ++s) {
             const bool post = pv_post != nullptr && (call >= SERL_TRIGGER_CALLS || (s == 5 && call == SERL_TRIGGER_CALLS - 1));
-            if (GUST) u[3] = gust ? plant_gust_offset(call, s, x[3]) : (real)0;
+            if (GUST) { u[3] = gust ? plant_gust_offset(call, s, x[3]) : (real)0; if (gust_up) u[3] = -u[3]; }
             if (STAB) plant_rhs_common_smem(x, u, fc, tab, post ? pv_post : pv);
             else plant_rhs_common(x, u, fc, tab, post ? pv_post : pv);
             double acc[NLIVE];
@@ -390,7 +391,7 @@ static __device__ __noinline__ void plant_step(const real* pv, double* X, const 
 #pragma unroll
         for (int s = 0; s < 6; ++s) {
             const bool post = pv_post != nullptr && (call >= SERL_TRIGGER_CALLS || (s == 5 && call == SERL_TRIGGER_CALLS - 1));
-            if (GUST) u[3] = gust ? plant_gust_offset(call, s, x[3]) : (real)0;
+            if (GUST) { u[3] = gust ? plant_gust_offset(call, s, x[3]) : (real)0; if (gust_up) u[3] = -u[3]; }
             if (STAB) plant_rhs_common_smem(x, u, f[s], tab, post ? pv_post : pv);
             else plant_rhs_common(x, u, f[s], tab, post ? pv_post : pv);
 #pragma unroll
@@ -475,7 +476,8 @@ struct Env {
     const double* ref_st;
     double t, ret, theta_trim;
     int fault, k;
-    bool done, gust;         // gust: SERL_MODE_GUST
+    bool done;
+    int gust;                // env_mode >> 24: 1 = SERL_MODE_GUST, 3 = with SERL_MODE_GUST_UP
 };
 
 #define DEG2RAD 0.017453292519943295   // numpy deg2rad multiplier (pi/180)
@@ -499,7 +501,7 @@ __device__ __forceinline__ void env_bind(Env& e, const RolloutArgs& a, int env, 
     const int post = (mode >> 16) & 0xff;
     e.pv_post = post ? pv_base + post * PLANT_NPV : nullptr;
     e.fault = (mode >> 8) & 0xff;
-    e.gust = (mode & SERL_MODE_GUST) != 0;
+    e.gust = (mode >> 24) & 3;
     e.ref_lv = a.ref_levels + (size_t)env * 2 * SERL_REF_BLOCKS;
     e.ref_st = a.ref_starts + (size_t)env * 2 * SERL_REF_BLOCKS;
     // theta_trim = rad2deg(theta) of reset()'s step output (phlabenv.py:317) — with the sensor-noise shim that output is noisy
@@ -579,7 +581,7 @@ static __device__ void env_step(Env& e, const RolloutArgs& ar, size_t traj, int 
     double xo[12];
 #pragma unroll
     for (int i = 0; i < 12; ++i) xo[i] = e.X[i];
-    plant_step<STAB, TMF, GUST>(e.pv, e.X, cmd, e.tab, ar.trace != nullptr, e.pv_post, (e.k + 1) | (GUST && e.gust ? PLANT_CALL_GUST : 0), taddr, active);
+    plant_step<STAB, TMF, GUST>(e.pv, e.X, cmd, e.tab, ar.trace != nullptr, e.pv_post, (e.k + 1) | (GUST && (e.gust & 1) ? PLANT_CALL_GUST | ((e.gust & 2) ? PLANT_CALL_GUST_UP : 0) : 0), taddr, active);
     if (!active) return;
     sensor_noise(ar, traj, e.k + 1, xo);
 

@@ -453,7 +453,7 @@ rollout_kernel_persist(RolloutArgs ar)
                         env_reset<TABS>(e, ar, env, obs, traj);
                     }
                 } else {
-                    e.done = true; e.k = 0; e.ret = 0.0; e.t = 0.0; e.fault = 0; e.gust = false; e.pv = pv_base; e.pv_post = nullptr; e.theta_trim = 0.0;
+                    e.done = true; e.k = 0; e.ret = 0.0; e.t = 0.0; e.fault = 0; e.gust = 0; e.pv = pv_base; e.pv_post = nullptr; e.theta_trim = 0.0;
                     e.ref_lv = ar.ref_levels; e.ref_st = ar.ref_starts;
 #pragma unroll
                     for (int i = 0; i < NX; ++i) e.X[i] = 0.0;
@@ -580,7 +580,8 @@ __global__ void plant_step_kernel(double* __restrict__ X, const double* __restri
     u[0] = cmd[3 * i]; u[1] = cmd[3 * i + 1]; u[2] = cmd[3 * i + 2];
     const int post = (variant[i] >> 16) & 0xff;
     plant_step<false, false, true>(plant_pv[variant[i] & 0xff], x, u, plant_tables_blob, false, post ? plant_pv[post] : nullptr,
-                                   (call ? call[i] : 0) | ((variant[i] & SERL_MODE_GUST) ? PLANT_CALL_GUST : 0));
+                                   (call ? call[i] : 0) | ((variant[i] & SERL_MODE_GUST) ? PLANT_CALL_GUST : 0) |
+                                       ((variant[i] & SERL_MODE_GUST_UP) ? PLANT_CALL_GUST_UP : 0));
 #pragma unroll
     for (int k = 0; k < NX; ++k) X[(size_t)i * NX + k] = x[k];
 }

@@ -424,7 +424,7 @@ rollout_kernel_tc(TcArgs ar)
             env_bind(e, r, env, pv_base, (size_t)actor * r.n_envs + env);
             env_reset<true>(e, r, env, obs, (size_t)actor * r.n_envs + env);
         } else {
-            e.done = true; e.k = 0; e.ret = 0.0; e.t = 0.0; e.fault = 0; e.gust = false; e.pv = pv_base; e.pv_post = nullptr; e.theta_trim = 0.0;
+            e.done = true; e.k = 0; e.ret = 0.0; e.t = 0.0; e.fault = 0; e.gust = 0; e.pv = pv_base; e.pv_post = nullptr; e.theta_trim = 0.0;
             e.ref_lv = r.ref_levels; e.ref_st = r.ref_starts;
 #pragma unroll
             for (int i = 0; i < NX; ++i) e.X[i] = 0.0;

@@ -21,14 +21,16 @@ MODES = {
     'cg-for': ('cg_for', 'none'), 'h2000-v150': ('h2000_v150', 'none'), 'h10000-v90': ('h10000_v90', 'none'),
     'cg-timed': ('cg_timed', 'none'),
     'gust': ('h2000_v90', 'none'),      # nominal dynamics + MODE_GUST (include/serl_b200.h); the env adds the sensor-noise shim
+    'test': ('h2000_v90', 'none'),      # envs/test: the same pulse with the opposite sign (MODE_GUST | MODE_GUST_UP), no shim
 }
 MODE_GUST = 1 << 24
+MODE_GUST_UP = 1 << 25
 
 
 def mode_code(mode):
     v, f = MODES[mode]
     post = PLANT_VARIANTS.index(POST_VARIANT[v]) if v in POST_VARIANT else 0
-    return PLANT_VARIANTS.index(v) | (FAULTS.index(f) << 8) | (post << 16) | (MODE_GUST if mode == 'gust' else 0)
+    return PLANT_VARIANTS.index(v) | (FAULTS.index(f) << 8) | (post << 16) | (MODE_GUST if mode in ('gust', 'test') else 0) | (MODE_GUST_UP if mode == 'test' else 0)
 
 
 def actor_shape(hidden, num_layers=3, activation='tanh', state_dim=7, action_dim=3):

@@ -57,16 +57,17 @@ def test_plant_step_kernel_matches_oracle(variant):
 
 @pytest.mark.skipif(not os.path.exists(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'oracle', '_ref', 'citation_gust.so')),
                     reason='needs the reference gust binary under oracle/_ref')
-def test_timed_plant_step_api_flies_the_gust_pulse_like_the_binary():
+@pytest.mark.parametrize('build', ['gust', 'test'])
+def test_timed_plant_step_api_flies_the_gust_pulse_like_the_binary(build):
     """serl_plant_step_timed with SERL_MODE_GUST (the per-step path of CitationEnv in 'gust' mode): one-step predictions from
     the binary's own states through both edges of the pulse (native calls 1996..2003, 2296..2303) and in its middle."""
     from serl_b200 import _native, rollout
     L = _native.lib()
     dev = torch.device('cuda:0')
     st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-    pl = OP.RefPlant('gust')
+    pl = OP.RefPlant(build)          # envs/test: the same pulse with the opposite sign
     X = pl.initial_state()
-    var = torch.tensor([rollout.mode_code('gust') & ~0xff00], dtype=torch.int32, device=dev)
+    var = torch.tensor([rollout.mode_code(build) & ~0xff00], dtype=torch.int32, device=dev)
     live = [0, 1, 2, 3, 4, 5, 6, 7, 9, 12, 15, 16, 17, 18]
     worst, changed = 0.0, 0
     for k in range(2306):

@@ -103,8 +103,10 @@ def test_noise_mode_and_time_triggered_modes_are_named():
     assert config.select_env('PHlab_attitude_cg-shift').mode == 'cg-timed'
     gust = config.select_env('PHlab_attitude_gust')
     assert gust.sensor_noise and gust.mode == 'gust' and gust.mode_code & (1 << 24)
+    test = config.select_env('PHlab_attitude_test')
+    assert not test.sensor_noise and test.mode == 'test' and (test.mode_code >> 24) == 3
     with pytest.raises(ValueError):
-        config.select_env('PHlab_attitude_test')
+        config.select_env('PHlab_attitude_nosuchmode')
 
 
 @pytest.mark.skipif(not os.path.exists(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'oracle', '_ref', 'citation_cg_timed.so')),

@@ -97,10 +97,12 @@ def test_generated_device_rhs_matches_reference_binary_vectors(devlib, variant):
 
 
 @pytest.mark.skipif(not os.path.isdir('/root/reference/envs'), reason='needs the reference tree (build container only)')
-def test_gust_build_is_the_nominal_rhs_with_an_angle_of_attack_offset(devlib, tmp_path):
+@pytest.mark.parametrize('build,sign', [('gust', 1.0), ('test', -1.0)])
+def test_gust_build_is_the_nominal_rhs_with_an_angle_of_attack_offset(devlib, tmp_path, build, sign):
     """envs/gust ("vertical gust of 15 ft/s at 20 s"): ode5 over the generated right-hand side with U[3] = atan(w / V) for the
     stages inside 20 s <= t <= 23 s (last stage of native call 1999, calls 2000..2299, first stage of call 2300) reproduces
-    the gust BINARY bit for bit (reference-order build) through both edges of the pulse."""
+    the gust BINARY bit for bit (reference-order build) through both edges of the pulse.  envs/test is the same pulse with the
+    opposite sign (U[3] = -atan(w / V))."""
     import math
     import shutil
     which, lib = devlib
@@ -108,7 +110,7 @@ def test_gust_build_is_the_nominal_rhs_with_an_angle_of_attack_offset(devlib, tm
         pytest.skip('double-precision check')
     D = ctypes.c_double
     so = tmp_path / 'gust.so'
-    shutil.copy('/root/reference/envs/gust/_citation.cpython-38-x86_64-linux-gnu.so', so)
+    shutil.copy('/root/reference/envs/%s/_citation.cpython-38-x86_64-linux-gnu.so' % build, so)
     ref = ctypes.CDLL(str(so))
     ref.step.argtypes = [ctypes.POINTER(D), ctypes.POINTER(D)]
     ref.initialize()
@@ -127,7 +129,7 @@ def test_gust_build_is_the_nominal_rhs_with_an_angle_of_attack_offset(devlib, tm
         f, x = [], X.copy()
         for s in range(6):
             out = (D * 19)()
-            lib.dev_rhs(0, (D * 19)(*x), (D * 4)(u[0], u[1], u[2], math.atan(w / x[3]) * 1.0 if on(call, s) else 0.0), out)
+            lib.dev_rhs(0, (D * 19)(*x), (D * 4)(u[0], u[1], u[2], sign * (math.atan(w / x[3]) * 1.0) if on(call, s) else 0.0), out)
             f.append(np.array(out[:]))
             x = X.copy()
             for i in idx:
