@@ -277,10 +277,10 @@ static __device__ __noinline__ void plant_step_nav(double* Xnav, const double* X
     }
 }
 
-// Stage loop fully unrolled (every f[j][li] load of a stage is independent, h*B folds to constants).  The right-hand side
-// is ONE __noinline__ function (the same code for every plant variant), so the compact state x[14] and the stage
-// derivatives f[6][14] live in local memory (896 B per thread, L1-resident).  The integrator state and the stage
-// combinations are double in every build; `real` (the type of the right-hand side) is double unless PLANT_F32.
+// Stage loop fully unrolled (h*B folds to constants).  The right-hand side is ONE __noinline__ function (the same code for
+// every plant variant), so the compact state x[14] and the stage derivative it writes are in local memory; the six stage
+// derivatives are kept in tensor memory (TMF, below) or, in traced launches, in local memory.  The integrator state and the
+// stage combinations are double in every build; `real` (the type of the right-hand side) is double unless PLANT_F32.
 // pv_post / call: time-triggered builds (cg_timed): the parameter row switches to pv_post when the model clock
 // call * 0.01 + c_s * 0.01 of a stage reaches 20 s: every stage from call SERL_TRIGGER_CALLS on, and the LAST stage (c = 1) of
 // call SERL_TRIGGER_CALLS - 1, whose time 19.99 + 0.01 already compares >= 20 in the binary.

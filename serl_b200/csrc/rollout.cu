@@ -6,14 +6,16 @@
 //   CitationEnv.step     (envs/phlabenv.py:430-482: action scaling :62-73, fault shims envs/{be,jr,sa,se}/citation.py,
 //                         reward :362-367, termination + penalty :391-399)                                fp64
 //   native plant step    (envs/<variant>/_citation*.so step @0x6030: 6-stage Dormand-Prince ode5, h = 0.01, RHS
-//                         generated from the binary by tools/lift -> csrc/gen/plant_rhs_{common,ice}.h)      fp64
+//                         generated from the binaries by tools/lift -> csrc/gen/plant_rhs_common.h)          fp64
 // and accumulates the episodic return (base/core/agent.py:129).  HBM is touched only at episode start
 // (genome, reference-signal parameters) and end (return, step count) unless a trace / action history is requested.
 //
 // Two actor implementations:
-//   rollout_kernel_warp<H>  warp-autonomous: a warp never synchronises with other warps.  The MLP is a register-tiled
-//                           GEMM inside the warp (lane = 1/4 of the output neurons x 4 envs, packed FFMA2, activations
-//                           exchanged with warp shuffles, weights broadcast from shared memory).  (h in {32,64,72,96,128})
+//   rollout_kernel_persist<H, TABS, GUST>  persistent grid, one CTA per SM.  The MLP is a register-tiled GEMM inside a warp
+//                           (lane = 1/4 of the output neurons x 4 envs, packed FFMA2, activations exchanged with warp
+//                           shuffles, weights broadcast from shared memory; h in {32,64,72,96,128}).  The CTA's warps take
+//                           their steps in lockstep (one barrier per step: shared instruction fetch), genomes arrive by bulk
+//                           TMA copies, the ode5 stage derivatives live in tensor memory.
 //   rollout_kernel_simple   every thread runs the whole MLP for its env (any h that fits); cross-check / fallback shape.
 #include "plant_env.cuh"
 
@@ -275,8 +277,8 @@ __global__ void genome_layout_kernel(const float* __restrict__ w, float* __restr
 // trajectories' state in HBM (Handoff), then its whole tasks, and LAST the tail segment, whose first part the previous
 // slot published long before: no slot ever waits in practice, and all SMs finish together (512 actors x 128 envs on
 // 148 SMs x 2 slots = 1.73 tasks per slot: two full rounds without the split).  When there are fewer tasks than
-// slots every task is flown whole by one slot.  Warps never synchronise inside a segment; the slot's warps meet at a
-// named barrier only to swap the genome, which ONE elected thread brings in with a bulk TMA copy.
+// slots every task is flown whole by one slot.  The genome of a slot is swapped by ONE elected thread with a bulk TMA copy;
+// the slot's warps meet at its named barrier for that and for the slot-uniform decisions of the lockstep loop (see there).
 // TABS: plant tables staged in shared memory (true) or read from global memory through L1 (false: h = 128, whose
 // 207 KB genome leaves no room for them).
 // GUST: the launch contains envs of the gust build (serl_rollout_desc.flags & SERL_ROLLOUT_GUST); the training instantiation
